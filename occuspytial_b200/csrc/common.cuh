@@ -1,0 +1,109 @@
+// common.cuh -- shared device helpers for the occuspytial_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define OCCU_PI 3.141592653589793238462643383279502884
+#define OCCU_PI_F 3.14159265358979f
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011).  A draw is addressed by logical
+// coordinates only -- (seed; chain, element, iteration, stage/block) -- so that the same seed gives
+// the same chains whatever the grid shape or the number of GPUs (reference contract: same
+// random_state => same chains, gibbs/tests/test_samplers.py:63-68).
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t ctr[4];
+    uint32_t key[2];
+    uint32_t buf[4];
+    int have;
+
+    // chain: global chain id, elem: site / visit row / vector slot, iter: sweep number,
+    // stage: which conditional (8 bits); the low 24 bits of ctr[3] count 128-bit blocks.
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t chain, uint32_t elem, uint32_t iter, uint32_t stage) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = chain;
+        ctr[1] = elem;
+        ctr[2] = iter;
+        ctr[3] = stage << 24;
+        have = 0;
+    }
+
+    __device__ __forceinline__ void refill() {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+        uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ k0;
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ k1;
+            c3 = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        buf[0] = c0;
+        buf[1] = c1;
+        buf[2] = c2;
+        buf[3] = c3;
+        ctr[3] += 1u;
+        have = 4;
+    }
+
+    __device__ __forceinline__ uint32_t next_u32() {
+        if (have == 0) refill();
+        have--;
+        // static indexing keeps buf[] in registers
+        return have == 3 ? buf[0] : have == 2 ? buf[1] : have == 1 ? buf[2] : buf[3];
+    }
+
+    // uniform on (0,1), 24 random bits, never 0 or 1
+    __device__ __forceinline__ float unif_f() { return ((float)(next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+    // uniform on (0,1), 53 random bits, never 0 or 1
+    __device__ __forceinline__ double unif_d() {
+        const uint32_t a = next_u32(), b = next_u32();
+        const uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);  // 53 bits
+        return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+    }
+
+    // standard normal, Box-Muller in FP64 (one value per call; only O(q) of these per chain-iteration)
+    __device__ __forceinline__ double normal_d() {
+        const double u1 = unif_d(), u2 = unif_d();
+        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+};
+
+template <typename T>
+struct RT;  // real-type dispatch for samplers that run in either precision
+template <>
+struct RT<float> {
+    static __device__ __forceinline__ float unif(Philox& g) { return g.unif_f(); }
+    static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return __logf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float erfc_(float x) { return erfcf(x); }
+    static __device__ __forceinline__ float cospi_(float x) { return cospif(x); }
+};
+template <>
+struct RT<double> {
+    static __device__ __forceinline__ double unif(Philox& g) { return g.unif_d(); }
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double erfc_(double x) { return erfc(x); }
+    static __device__ __forceinline__ double cospi_(double x) { return cospi(x); }
+};
+
+// logistic function in FP64, safe for large |x| (scipy.special.expit semantics)
+__device__ __forceinline__ double expit_d(double x) {
+    if (x >= 0.0) return 1.0 / (1.0 + exp(-x));
+    const double e = exp(x);
+    return e / (1.0 + e);
+}
+
+// Phi(x) in FP64 (scipy.special.ndtr semantics)
+__device__ __forceinline__ double ndtr_d(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }

@@ -1,0 +1,1204 @@
+// engine.cu -- lock-step multi-chain Gibbs sweep for OccuSpytial's samplers on B200 (sm_100a).
+//
+// One engine = one GPU's shard of chains.  The chain axis is the SIMD axis: every per-chain vector is
+// stored chain-minor ([element][chain]) so that a warp is 32 chains looking at the same site / visit
+// row, shared data (X, K, W, y) is a warp-uniform broadcast and all per-chain traffic is coalesced.
+//
+// One iteration (same Markov transition as <Sampler>.step(), logit.py:254-266, re-cut at z so that
+// every conditional that only needs (z, alpha, psi) shares one pass over the sites):
+//   1. psi   = [X K] theta                       DMMA GEMM            (logit.py:201, 485)
+//   2. site pass: z | psi, alpha   (skipped at iteration 0: z comes from the data, base.py:113-118)
+//                 omega_a | z, alpha -> partial sums of W_e' Om_a W_e and W_e'(y_e - 1/2)
+//                 omega_b | psi                                       (logit.py:180-204, 234-252)
+//   3. [G | H] = [Omega' Z | kd' U]              DMMA GEMM            (logit.py:222-231, 327-335, 481)
+//   4. reduce the alpha partial sums (fixed order, no float atomics)
+//   5. per-chain solve: tau, eta, beta, alpha    (logit.py:206-232, 478-485; distributions.pyx:42-110)
+// The draw recorded after step 5 is (alpha, beta, tau) exactly as Chain.append sees it (base.py:238-239).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/occu_b200.h"
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "samplers.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return -1;
+}
+#define CUDA_OK(call)                                                                  \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) return set_err("CUDA error %s at %s", cudaGetErrorString(_e), #call); \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// Philox stage ids (ctr[3] high byte)
+enum { ST_Z = 0, ST_OMEGA_B = 1, ST_OMEGA_A = 2, ST_TAU = 3, ST_NORMALS = 4, ST_EPS = 5, ST_HOOK = 6 };
+
+constexpr int SITE_TILE = 32;    // sites per CTA in the site pass
+constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
+constexpr int SOLVE_THREADS = 128;
+constexpr int MAX_SMALL = 32;    // max p and r
+
+struct Control {
+    uint32_t iter;     // iteration counter (Philox coordinate)
+    int32_t first;     // 1 until the first site pass has run (z taken from the data)
+    int32_t rec_index; // draw index to record at, < 0: none
+    int32_t fails;     // number of chains with a numerical failure
+};
+
+struct HParams {
+    double tau_rate, tau_shape;
+    double a_prec[MAX_SMALL * MAX_SMALL], b_prec[MAX_SMALL * MAX_SMALL];
+    double a_pm[MAX_SMALL], b_pm[MAX_SMALL];  // prec @ mu
+};
+
+// device view of an engine (passed to kernels by value)
+struct View {
+    int model, n, p, r, q, pq, V, C, Cp, chain_offset;
+    int n_pad, kq_pad, M, M_pad, ldg, n_tiles, NV;
+    uint64_t seed;
+    const double* W;
+    const uint8_t* y;
+    const int32_t* visit_ptr;
+    const uint8_t* site_class;
+    const double* Qrsr;
+    const HParams* hp;
+    double* UT;     // [kq_pad][n_pad]
+    double* ZU;     // [n_pad][ldg]   Z | U
+    double* theta;  // [kq_pad][Cp]   beta rows then eta rows
+    double* alpha;  // [r][Cp]
+    double* tau;    // [Cp]
+    double* psi;    // [n_pad][Cp]
+    double* omega;  // [n_pad][Cp]
+    double* kd;     // [n_pad][Cp]
+    uint8_t* z;     // [n][Cp]
+    double* G;      // [Cp][ldg]
+    double* apart;  // [n_tiles][NV][Cp]
+    double* asum;   // [NV][Cp]
+    double* zprob;  // [n][Cp] or NULL
+    int32_t* status;  // [Cp]
+    Control* ctl;
+};
+
+struct occu_engine {
+    View v;
+    occu_problem_t prob;
+    int pg_fp64, debug;
+    long long launches;
+    char* ws;
+    size_t ws_bytes;
+};
+
+// ------------------------------------------------------------------------------------------------
+// layout / workspace carving (shared by occu_workspace_bytes and occu_create)
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+    char* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+static int fill_dims(const occu_problem_t* P, View& v) {
+    if (!P) return set_err("null problem");
+    if (P->abi_version != OCCU_ABI_VERSION) return set_err("ABI version mismatch");
+    if (P->model != OCCU_LOGIT_RSR) return set_err("model not implemented in this build");
+    if (P->n < 1 || P->p < 1 || P->r < 1 || P->chains < 1 || P->V < 0) return set_err("bad dimensions");
+    if (P->p > MAX_SMALL || P->r > 8) return set_err("p must be <= 32 and r <= 8");
+    if (P->q < 1) return set_err("RSR model needs q >= 1");
+    v.model = P->model;
+    v.n = P->n; v.p = P->p; v.r = P->r; v.q = P->q; v.V = P->V;
+    v.pq = P->p + P->q;
+    v.C = P->chains;
+    v.Cp = round_up(P->chains, CHAIN_TILE);
+    v.chain_offset = P->chain_offset;
+    v.seed = P->seed;
+    v.n_pad = round_up(P->n, 128);
+    v.kq_pad = round_up(v.pq, dgemm::BK);
+    v.M = v.pq * (v.pq + 1) / 2;
+    v.M_pad = round_up(v.M, dgemm::BN);
+    v.ldg = v.M_pad + round_up(v.pq, dgemm::BN);
+    v.n_tiles = (P->n + SITE_TILE - 1) / SITE_TILE;
+    v.NV = P->r * (P->r + 1) / 2 + P->r;
+    // solve kernel keeps the packed joint Gram + H + a few vectors in shared memory
+    const size_t solve_smem = ((size_t)v.M + 6 * (size_t)v.pq + 64) * 8;
+    if (solve_smem > 220 * 1024) return set_err("p + q too large for the shared-memory solve (p+q <= ~230)");
+    return 0;
+}
+
+static void carve(View& v, char* base, size_t* total, int debug) {
+    Carver c{base, 0};
+    const size_t Cp = v.Cp;
+    v.hp = c.take<HParams>(1);
+    v.ctl = c.take<Control>(1);
+    v.W = c.take<double>((size_t)v.V * v.r + 1);
+    v.y = c.take<uint8_t>((size_t)v.V + 1);
+    v.visit_ptr = c.take<int32_t>((size_t)v.n + 1);
+    v.site_class = c.take<uint8_t>(v.n);
+    v.Qrsr = c.take<double>((size_t)v.q * v.q);
+    v.UT = c.take<double>((size_t)v.kq_pad * v.n_pad);
+    v.ZU = c.take<double>((size_t)v.n_pad * v.ldg);
+    v.theta = c.take<double>((size_t)v.kq_pad * Cp);
+    v.alpha = c.take<double>((size_t)v.r * Cp);
+    v.tau = c.take<double>(Cp);
+    v.psi = c.take<double>((size_t)v.n_pad * Cp);
+    v.omega = c.take<double>((size_t)v.n_pad * Cp);
+    v.kd = c.take<double>((size_t)v.n_pad * Cp);
+    v.z = c.take<uint8_t>((size_t)v.n * Cp);
+    v.G = c.take<double>(Cp * (size_t)v.ldg);
+    v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
+    v.asum = c.take<double>((size_t)v.NV * Cp);
+    v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
+    v.status = c.take<int32_t>(Cp);
+    *total = align_up(c.off, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels
+// ------------------------------------------------------------------------------------------------
+// UT[a][i] = U[i][a], ZU[i][vech(a,b)] = U[i][a] U[i][b], ZU[i][M_pad + a] = U[i][a], U = [X K]
+__global__ void build_design_kernel(View v, const double* __restrict__ X, const double* __restrict__ K) {
+    const int i = blockIdx.x;
+    extern __shared__ double u[];
+    for (int a = threadIdx.x; a < v.pq; a += blockDim.x)
+        u[a] = (a < v.p) ? X[(size_t)i * v.p + a] : K[(size_t)i * v.q + (a - v.p)];
+    __syncthreads();
+    for (int a = threadIdx.x; a < v.pq; a += blockDim.x) {
+        v.UT[(size_t)a * v.n_pad + i] = u[a];
+        v.ZU[(size_t)i * v.ldg + v.M_pad + a] = u[a];
+    }
+    for (int m = threadIdx.x; m < v.M; m += blockDim.x) {
+        int a = (int)((sqrtf(8.0f * (float)m + 1.0f) - 1.0f) * 0.5f);
+        while (a * (a + 1) / 2 > m) a--;
+        while ((a + 1) * (a + 2) / 2 <= m) a++;
+        const int b = m - a * (a + 1) / 2;
+        v.ZU[(size_t)i * v.ldg + m] = u[a] * u[b];
+    }
+}
+
+// z from the data (base.py:113-118): 0 at surveyed-never-detected sites, 1 elsewhere; kd = z - 1/2
+__global__ void reset_z_kernel(View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)v.n * v.Cp;
+    if (idx >= total) return;
+    const int i = (int)(idx / v.Cp);
+    const uint8_t zc = v.site_class[i] == OCCU_SITE_NOT_OBS ? 0 : 1;
+    v.z[idx] = zc;
+    v.kd[idx] = (double)zc - 0.5;
+}
+
+__global__ void set_control_kernel(Control* c, uint32_t iter, int first, int rec_index, int clear_fails) {
+    c->iter = iter;
+    c->first = first;
+    c->rec_index = rec_index;
+    if (clear_fails) c->fails = 0;
+}
+
+__global__ void advance_kernel(Control* c) {
+    c->iter += 1;
+    c->first = 0;
+    if (c->rec_index >= 0) c->rec_index += 1;
+}
+
+// chain-major [C][d] -> chain-minor [d][Cp]; padded chains replicate chain (c mod C)
+template <typename T>
+__global__ void to_chain_minor_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int Cp, int d) {
+    __shared__ T tile[32][33];
+    const int c0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, e = e0 + threadIdx.x;
+        if (c < Cp && e < d) tile[j][threadIdx.x] = src[(size_t)(c % C) * d + e];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int e = e0 + j, c = c0 + threadIdx.x;
+        if (c < Cp && e < d) dst[(size_t)e * Cp + c] = tile[threadIdx.x][j];
+    }
+}
+
+template <typename T>
+__global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int Cp, int d) {
+    __shared__ T tile[32][33];
+    const int c0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int e = e0 + j, c = c0 + threadIdx.x;
+        if (c < Cp && e < d) tile[j][threadIdx.x] = src[(size_t)e * Cp + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, e = e0 + threadIdx.x;
+        if (c < C && e < d) dst[(size_t)c * d + e] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// site pass (logit): z-update, omega_a draws + alpha partial sums, omega_b draw
+// ------------------------------------------------------------------------------------------------
+template <int R, typename PGT>
+__global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View v) {
+    constexpr int NA = R * (R + 1) / 2, NV = NA + R;
+    const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
+    const int tile = blockIdx.x;
+    const int i0 = tile * SITE_TILE;
+    const int i1 = min(i0 + SITE_TILE, v.n);
+    const uint32_t iter = v.ctl->iter;
+    const bool first = v.ctl->first != 0;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const size_t Cp = v.Cp;
+
+    double al[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) al[k] = v.alpha[(size_t)k * Cp + c];
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.0;
+
+    for (int i = i0; i < i1; i++) {
+        const int cls = v.site_class[i];
+        const size_t off = (size_t)i * Cp + c;
+        const double psi = v.psi[off];
+        const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
+        int zc;
+        if (first) {
+            zc = v.z[off];
+        } else {
+            if (cls == OCCU_SITE_OBS) {
+                zc = 1;
+            } else {
+                double pr = expit_d(psi);  // logit.py:241 / 249
+                if (cls == OCCU_SITE_NOT_OBS) {
+                    double prod = 1.0;  // logit.py:242-243: prod_j expit(-w_ij alpha)
+                    for (int vv = v0; vv < v1; vv++) {
+                        double lin = 0.0;
+#pragma unroll
+                        for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                        prod *= expit_d(-lin);
+                    }
+                    const double num = pr * prod;
+                    pr = num / ((1.0 - pr) + num);  // logit.py:244-245
+                }
+                if (v.zprob) v.zprob[off] = pr;
+                Philox g;
+                g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
+                zc = g.unif_d() < pr ? 1 : 0;  // logit.py:246 / 250
+            }
+            v.z[off] = (uint8_t)zc;
+            v.kd[off] = (double)zc - 0.5;  // logit.py:252
+        }
+        if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
+            // omega_a ~ PG(1, w_ij alpha) over the visits of occupied surveyed sites (logit.py:187-193)
+            for (int vv = v0; vv < v1; vv++) {
+                double w[R];
+                double lin = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    w[k] = v.W[(size_t)vv * R + k];
+                    lin += w[k] * al[k];
+                }
+                Philox g;
+                g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
+                const double om = (double)pg1_draw<PGT>((PGT)lin, g);
+                const double yk = (double)v.y[vv] - 0.5;
+                int idx = 0;
+#pragma unroll
+                for (int a = 0; a < R; a++) {
+#pragma unroll
+                    for (int b = 0; b <= a; b++) acc[idx++] += om * w[a] * w[b];  // logit.py:222
+                }
+#pragma unroll
+                for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;  // logit.py:223
+            }
+        }
+        Philox g;
+        g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
+        v.omega[off] = (double)pg1_draw<PGT>((PGT)psi, g);  // logit.py:201-204
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
+}
+
+// Variant used by occu_debug_gaussian_half when omega_a is injected: alpha partial sums only.
+template <int R>
+__global__ void __launch_bounds__(CHAIN_TILE) alpha_partials_injected_kernel(const View v, const double* __restrict__ omega_a_cm) {
+    constexpr int NA = R * (R + 1) / 2, NV = NA + R;
+    const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
+    const int tile = blockIdx.x;
+    const int i0 = tile * SITE_TILE;
+    const int i1 = min(i0 + SITE_TILE, v.n);
+    const size_t Cp = v.Cp;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.0;
+    const double* oma = omega_a_cm + (size_t)(c % v.C) * v.V;
+    for (int i = i0; i < i1; i++) {
+        const int cls = v.site_class[i];
+        if (cls == OCCU_SITE_NOT_SURVEYED || !v.z[(size_t)i * Cp + c]) continue;
+        for (int vv = v.visit_ptr[i]; vv < v.visit_ptr[i + 1]; vv++) {
+            double w[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) w[k] = v.W[(size_t)vv * R + k];
+            const double om = oma[vv];
+            const double yk = (double)v.y[vv] - 0.5;
+            int idx = 0;
+#pragma unroll
+            for (int a = 0; a < R; a++) {
+#pragma unroll
+                for (int b = 0; b <= a; b++) acc[idx++] += om * w[a] * w[b];
+            }
+#pragma unroll
+            for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
+}
+
+// asum[k][c] = sum_tile apart[tile][k][c], fixed order
+__global__ void reduce_partials_kernel(const View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)v.NV * v.Cp;
+    if (idx >= per) return;
+    double s = 0.0;
+    for (int t = 0; t < v.n_tiles; t++) s += v.apart[(size_t)t * per + idx];
+    v.asum[idx] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-chain solve: tau, eta, beta, alpha
+// ------------------------------------------------------------------------------------------------
+struct SolveDebug {
+    const double* normals;  // [C][q+p+r] or NULL
+    const double* tau_in;   // [C] or NULL
+    occu_debug_out_t out;
+    int enabled;
+};
+
+__device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // b <= a
+
+// In-place Cholesky of the d x d block whose (i, j) entry (j <= i) lives at A[tri(o + i, o + j)].
+// Returns false (uniformly) on a non-positive pivot.
+__device__ bool block_cholesky_packed(double* A, int o, int d, int tid, int nthreads) {
+    for (int j = 0; j < d; j++) {
+        __syncthreads();
+        const double piv = A[tri(o + j, o + j)];
+        if (!(piv > 0.0)) return false;
+        const double dj = sqrt(piv);
+        const double inv = 1.0 / dj;
+        __syncthreads();
+        for (int i = j + tid; i < d; i += nthreads) {
+            if (i == j) A[tri(o + j, o + j)] = dj;
+            else A[tri(o + i, o + j)] *= inv;
+        }
+        __syncthreads();
+        const int m = d - 1 - j;
+        const int cnt = m * (m + 1) / 2;
+        for (int t = tid; t < cnt; t += nthreads) {
+            int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ii * (ii + 1) / 2 > t) ii--;
+            while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
+            const int kk = t - ii * (ii + 1) / 2;
+            const int i = j + 1 + ii, k = j + 1 + kk;
+            A[tri(o + i, o + k)] -= A[tri(o + i, o + j)] * A[tri(o + k, o + j)];
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Sequential small dense solve by one thread: x = P^-1 b + L^-T z, P = L L' (full d x d row-major in S,
+// lower triangle overwritten by L).  Returns false on a non-positive pivot.  distributions.pyx:88-105.
+__device__ bool small_precision_mvnorm(double* S, int d, const double* b, const double* zn, double* x, double* tmp) {
+    for (int j = 0; j < d; j++) {
+        double s = S[j * d + j];
+        for (int k = 0; k < j; k++) s -= S[j * d + k] * S[j * d + k];
+        if (!(s > 0.0)) return false;
+        const double dj = sqrt(s);
+        S[j * d + j] = dj;
+        for (int i = j + 1; i < d; i++) {
+            double t = S[i * d + j];
+            for (int k = 0; k < j; k++) t -= S[i * d + k] * S[j * d + k];
+            S[i * d + j] = t / dj;
+        }
+    }
+    for (int i = 0; i < d; i++) {  // L y = b
+        double t = b[i];
+        for (int k = 0; k < i; k++) t -= S[i * d + k] * tmp[k];
+        tmp[i] = t / S[i * d + i];
+    }
+    for (int i = d - 1; i >= 0; i--) {  // L' x = y + z
+        double t = tmp[i] + zn[i];
+        for (int k = i + 1; k < d; k++) t -= S[k * d + i] * x[k];
+        x[i] = t / S[i * d + i];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
+                                                                         double* rec_alpha, double* rec_beta,
+                                                                         double* rec_tau, int rec_capacity) {
+    extern __shared__ double sm[];
+    const int c = blockIdx.x, tid = threadIdx.x, T = SOLVE_THREADS;
+    const int p = v.p, q = v.q, r = v.r, pq = v.pq, M = v.M;
+    const size_t Cp = v.Cp;
+    const HParams* hp = v.hp;
+    double* Gs = sm;             // [M] packed lower triangle of the joint Gram over [beta; eta]
+    double* h = Gs + M;          // [pq]  U'(z - 1/2)
+    double* th = h + pq;         // [pq]  current beta, eta
+    double* rhs = th + pq;       // [2*pq] two right-hand sides
+    double* nrm = rhs + 2 * pq;  // [pq + r] normals
+    double* red = nrm + pq + MAX_SMALL;  // [T/32 + 2] reduction scratch
+    __shared__ double small_S[MAX_SMALL * MAX_SMALL];
+    __shared__ double small_b[MAX_SMALL], small_x[MAX_SMALL], small_t[MAX_SMALL];
+    __shared__ int ok_flag;
+
+    const uint32_t iter = v.ctl->iter;
+    const int rec_index = v.ctl->rec_index;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const int cr = c % v.C;  // chain whose injected values a padded chain replicates
+
+    const double* Grow = v.G + (size_t)c * v.ldg;
+    for (int m = tid; m < M; m += T) Gs[m] = Grow[m];
+    for (int a = tid; a < pq; a += T) {
+        h[a] = Grow[v.M_pad + a];
+        th[a] = v.theta[(size_t)a * Cp + c];
+    }
+    // normals: eta (q), beta (p), alpha (r)
+    for (int k = tid; k < pq + r; k += T) {
+        double val;
+        if (dbg.normals) {
+            val = dbg.normals[(size_t)cr * (pq + r) + k];
+        } else {
+            Philox g;
+            g.init(v.seed, gc, (uint32_t)k, iter, ST_NORMALS);
+            val = g.normal_d();
+        }
+        nrm[k] = val;
+    }
+    if (tid == 0) ok_flag = 1;
+    __syncthreads();
+
+    // ---- tau | eta   (logit.py:206-209) ----
+    {
+        double part = 0.0;
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            part += th[p + i] * v.Qrsr[idx] * th[p + j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((tid & 31) == 0) red[tid >> 5] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double quad = 0.0;
+            for (int w = 0; w < T / 32; w++) quad += red[w];
+            const double rate = 0.5 * quad + hp->tau_rate;
+            double tau;
+            if (dbg.tau_in) {
+                tau = dbg.tau_in[cr];
+            } else {
+                Philox g;
+                g.init(v.seed, gc, 0u, iter, ST_TAU);
+                tau = gamma_draw(hp->tau_shape, g) / rate;
+            }
+            red[T / 32] = tau;
+            if (dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
+        }
+        __syncthreads();
+    }
+    const double tau = red[T / 32];
+
+    // ---- eta | .   Lambda = K' Om K + tau Qrsr,  b = K'k - (K' Om X) beta   (logit.py:478-485, 327-336) ----
+    for (int idx = tid; idx < q * q; idx += T) {
+        const int i = idx / q, j = idx - i * q;
+        if (j <= i) Gs[tri(p + i, p + j)] += tau * v.Qrsr[idx];
+    }
+    for (int i = tid; i < q; i += T) {
+        double b = h[p + i];
+        for (int a = 0; a < p; a++) b -= Gs[tri(p + i, a)] * th[a];
+        rhs[i] = b;
+    }
+    __syncthreads();
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.eta_prec)
+            for (int idx = tid; idx < q * q; idx += T) {
+                const int i = idx / q, j = idx - i * q;
+                dbg.out.eta_prec[(size_t)c * q * q + idx] = (j <= i) ? Gs[tri(p + i, p + j)] : Gs[tri(p + j, p + i)];
+            }
+        if (dbg.out.eta_b)
+            for (int i = tid; i < q; i += T) dbg.out.eta_b[(size_t)c * q + i] = rhs[i];
+    }
+    const bool pd = block_cholesky_packed(Gs, p, q, tid, T);
+    if (!pd) {
+        if (tid == 0) {
+            v.status[c] = 1;
+            if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+        }
+        return;  // chain is frozen at its previous state; the failure is reported to the host
+    }
+    if (dbg.enabled && dbg.out.eta_chol && c < v.C)
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            dbg.out.eta_chol[(size_t)c * q * q + idx] = (j <= i) ? Gs[tri(p + i, p + j)] : 0.0;
+        }
+    // forward: L y = b (column sweep)
+    for (int j = 0; j < q; j++) {
+        __syncthreads();
+        const double yj = rhs[j] / Gs[tri(p + j, p + j)];
+        __syncthreads();
+        if (tid == 0) rhs[j] = yj;
+        for (int i = j + 1 + tid; i < q; i += T) rhs[i] -= Gs[tri(p + i, p + j)] * yj;
+    }
+    __syncthreads();
+    // backward with two right-hand sides: L' m = y (mean) and L' e = normals
+    double* rhs2 = rhs + pq;
+    for (int i = tid; i < q; i += T) rhs2[i] = nrm[i];
+    for (int j = q - 1; j >= 0; j--) {
+        __syncthreads();
+        const double d = Gs[tri(p + j, p + j)];
+        const double mj = rhs[j] / d, ej = rhs2[j] / d;
+        __syncthreads();
+        if (tid == 0) {
+            rhs[j] = mj;
+            rhs2[j] = ej;
+        }
+        for (int i = tid; i < j; i += T) {
+            const double l = Gs[tri(p + j, p + i)];
+            rhs[i] -= l * mj;
+            rhs2[i] -= l * ej;
+        }
+    }
+    __syncthreads();
+    if (dbg.enabled && dbg.out.eta_mean && c < v.C)
+        for (int i = tid; i < q; i += T) dbg.out.eta_mean[(size_t)c * q + i] = rhs[i];
+    for (int i = tid; i < q; i += T) th[p + i] = rhs[i] + rhs2[i];  // eta = mean + L^-T eps
+    __syncthreads();
+
+    // ---- beta | .   A = X' Om X + b_prec,  b = X'k - (X' Om K) eta + b_prec b_mu   (logit.py:226-232) ----
+    for (int idx = tid; idx < p * p; idx += T) {
+        const int a = idx / p, b = idx - a * p;
+        small_S[idx] = ((b <= a) ? Gs[tri(a, b)] : Gs[tri(b, a)]) + hp->b_prec[idx];
+    }
+    for (int a = tid; a < p; a += T) {
+        double b = h[a] + hp->b_pm[a];
+        for (int j = 0; j < q; j++) b -= Gs[tri(p + j, a)] * th[p + j];
+        small_b[a] = b;
+    }
+    __syncthreads();
+    // NOTE: rows p.. of Gs columns < p are untouched by the Cholesky (it only rewrites the KK block)
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.beta_prec)
+            for (int idx = tid; idx < p * p; idx += T) dbg.out.beta_prec[(size_t)c * p * p + idx] = small_S[idx];
+        if (dbg.out.beta_b)
+            for (int a = tid; a < p; a += T) dbg.out.beta_b[(size_t)c * p + a] = small_b[a];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (small_precision_mvnorm(small_S, p, small_b, nrm + q, small_x, small_t)) {
+            for (int a = 0; a < p; a++) th[a] = small_x[a];
+        } else {
+            ok_flag = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- alpha | .   A = W_e' Om_a W_e + a_prec,  b = W_e'(y_e - 1/2) + a_prec a_mu   (logit.py:219-224) ----
+    const int NA = r * (r + 1) / 2;
+    for (int idx = tid; idx < r * r; idx += T) {
+        const int a = idx / r, b = idx - a * r;
+        const int k = (b <= a) ? tri(a, b) : tri(b, a);
+        small_S[idx] = v.asum[(size_t)k * Cp + c] + hp->a_prec[idx];
+    }
+    for (int a = tid; a < r; a += T) small_b[a] = v.asum[(size_t)(NA + a) * Cp + c] + hp->a_pm[a];
+    __syncthreads();
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.alpha_prec)
+            for (int idx = tid; idx < r * r; idx += T) dbg.out.alpha_prec[(size_t)c * r * r + idx] = small_S[idx];
+        if (dbg.out.alpha_b)
+            for (int a = tid; a < r; a += T) dbg.out.alpha_b[(size_t)c * r + a] = small_b[a];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (!small_precision_mvnorm(small_S, r, small_b, nrm + pq, small_x, small_t)) ok_flag = 0;
+    }
+    __syncthreads();
+    if (!ok_flag) {
+        if (tid == 0) {
+            v.status[c] = 1;
+            if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+        }
+        return;
+    }
+
+    // ---- commit state, record the draw (Chain.append, chain.py:56-74) ----
+    for (int a = tid; a < pq; a += T) v.theta[(size_t)a * Cp + c] = th[a];
+    for (int a = tid; a < r; a += T) v.alpha[(size_t)a * Cp + c] = small_x[a];
+    if (tid == 0) v.tau[c] = tau;
+    if (rec_alpha && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+        const size_t row = (size_t)c * rec_capacity + rec_index;
+        for (int a = tid; a < r; a += T) rec_alpha[row * r + a] = small_x[a];
+        for (int a = tid; a < p; a += T) rec_beta[row * p + a] = th[a];
+        if (tid == 0) rec_tau[row] = tau;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone primitives
+// ------------------------------------------------------------------------------------------------
+template <typename PGT>
+__global__ void pg1_kernel(const double* __restrict__ c, size_t count, uint64_t seed, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Philox g;
+    g.init(seed, (uint32_t)(i >> 32), (uint32_t)i, 0u, ST_HOOK);
+    out[i] = (double)pg1_draw<PGT>((PGT)c[i], g);
+}
+
+__global__ void truncnorm_kernel(const double* __restrict__ loc, const uint8_t* __restrict__ positive,
+                                 const double* __restrict__ u, size_t count, uint64_t seed, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (u) {
+        out[i] = truncnorm_icdf(loc[i], positive[i] != 0, u[i]);
+    } else {
+        Philox g;
+        g.init(seed, (uint32_t)(i >> 32), (uint32_t)i, 0u, ST_HOOK);
+        out[i] = truncnorm_draw(loc[i], positive[i] != 0, g);
+    }
+}
+
+__global__ void gamma_kernel(const double* __restrict__ shape, const double* __restrict__ rate, size_t count,
+                             uint64_t seed, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Philox g;
+    g.init(seed, (uint32_t)(i >> 32), (uint32_t)i, 0u, ST_HOOK);
+    out[i] = gamma_draw(shape[i], g) / rate[i];
+}
+
+// one CTA per system; P (full row-major) is staged packed in shared memory
+__global__ void __launch_bounds__(SOLVE_THREADS) precision_mvnorm_kernel(int d, const double* __restrict__ b,
+                                                                          double* __restrict__ P,
+                                                                          const double* __restrict__ z, uint64_t seed,
+                                                                          double* __restrict__ x, int* fails) {
+    extern __shared__ double sm[];
+    const int s = blockIdx.x, tid = threadIdx.x, T = SOLVE_THREADS;
+    double* A = sm;                   // packed lower
+    double* rhs = A + d * (d + 1) / 2;  // [d]
+    double* Ps = P + (size_t)s * d * d;
+    for (int idx = tid; idx < d * d; idx += T) {
+        const int i = idx / d, j = idx - i * d;
+        if (j <= i) A[tri(i, j)] = Ps[idx];
+    }
+    __syncthreads();
+    if (!block_cholesky_packed(A, 0, d, tid, T)) {
+        if (tid == 0) atomicAdd(fails, 1);
+        return;
+    }
+    for (int idx = tid; idx < d * d; idx += T) {
+        const int i = idx / d, j = idx - i * d;
+        if (j <= i) Ps[idx] = A[tri(i, j)];  // reference overwrites prec with its factor (distributions.pyx:100)
+    }
+    for (int i = tid; i < d; i += T) rhs[i] = b[(size_t)s * d + i];
+    for (int j = 0; j < d; j++) {
+        __syncthreads();
+        const double yj = rhs[j] / A[tri(j, j)];
+        __syncthreads();
+        if (tid == 0) rhs[j] = yj;
+        for (int i = j + 1 + tid; i < d; i += T) rhs[i] -= A[tri(i, j)] * yj;
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += T) {
+        double zn;
+        if (z) {
+            zn = z[(size_t)s * d + i];
+        } else {
+            Philox g;
+            g.init(seed, (uint32_t)s, (uint32_t)i, 0u, ST_HOOK);
+            zn = g.normal_d();
+        }
+        rhs[i] += zn;
+    }
+    for (int j = d - 1; j >= 0; j--) {
+        __syncthreads();
+        const double xj = rhs[j] / A[tri(j, j)];
+        __syncthreads();
+        if (tid == 0) rhs[j] = xj;
+        for (int i = tid; i < j; i += T) rhs[i] -= A[tri(j, i)] * xj;
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += T) x[(size_t)s * d + i] = rhs[i];
+}
+
+__global__ void sums_to_zero_kernel(int d, const double* __restrict__ x, const double* __restrict__ z,
+                                    double* __restrict__ out) {
+    // one warp per row, fixed-order tree reduction
+    const int row = blockIdx.x, lane = threadIdx.x;
+    const double* xr = x + (size_t)row * d;
+    const double* zr = z + (size_t)row * d;
+    double sx = 0.0, sz = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        sx += xr[i];
+        sz += zr[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    const double a = -sx / sz;
+    for (int i = lane; i < d; i += 32) out[(size_t)row * d + i] = xr[i] + a * zr[i];
+}
+
+// per (chain, component): whole-chain and split-half moments + autocovariances
+__global__ void chain_summaries_kernel(const double* __restrict__ rec, int chains, int draws, int dim, int max_lag,
+                                       double* __restrict__ out) {
+    const int cd = blockIdx.x;  // chain * dim + component
+    const int c = cd / dim, k = cd - c * dim;
+    const double* x = rec + (size_t)c * draws * dim + k;
+    const int W = 6 + max_lag + 1;
+    double* o = out + (size_t)cd * W;
+    __shared__ double s_mean;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, T = blockDim.x;
+    auto block_sum = [&](double val) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = val;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < T / 32; w++) tot += red[w];
+        return tot;
+    };
+    const int half = draws / 2;
+    // ranges: whole, first half, second half
+    for (int part = 0; part < 3; part++) {
+        const int lo = part == 2 ? draws - half : 0;
+        const int hi = part == 1 ? half : draws;
+        const int cnt = hi - lo;
+        double s = 0.0;
+        for (int t = lo + tid; t < hi; t += T) s += x[(size_t)t * dim];
+        const double mean = cnt > 0 ? block_sum(s) / cnt : 0.0;
+        double m2 = 0.0;
+        for (int t = lo + tid; t < hi; t += T) {
+            const double dlt = x[(size_t)t * dim] - mean;
+            m2 += dlt * dlt;
+        }
+        m2 = block_sum(m2);
+        if (tid == 0) {
+            o[2 * part] = mean;
+            o[2 * part + 1] = m2;
+            if (part == 0) s_mean = mean;
+        }
+        __syncthreads();
+    }
+    const double mean = s_mean;
+    for (int lag = 0; lag <= max_lag; lag++) {
+        double s = 0.0;
+        for (int t = tid; t + lag < draws; t += T) s += (x[(size_t)t * dim] - mean) * (x[(size_t)(t + lag) * dim] - mean);
+        s = block_sum(s);
+        if (tid == 0) o[6 + lag] = s / draws;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side drivers
+// ------------------------------------------------------------------------------------------------
+template <typename PGT>
+static void launch_site_pass(occu_engine* e, cudaStream_t st) {
+    const View& v = e->v;
+    dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
+    switch (v.r) {
+#define CASE(R) case R: site_pass_logit_kernel<R, PGT><<<grid, CHAIN_TILE, 0, st>>>(v); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    e->launches++;
+}
+
+static void launch_alpha_injected(occu_engine* e, const double* omega_a, cudaStream_t st) {
+    const View& v = e->v;
+    dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
+    switch (v.r) {
+#define CASE(R) case R: alpha_partials_injected_kernel<R><<<grid, CHAIN_TILE, 0, st>>>(v, omega_a); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    e->launches++;
+}
+
+static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
+    const View& v = e->v;
+    dgemm::Args a;
+    a.A1 = a.A2 = v.UT; a.B = v.theta; a.Out = v.psi;
+    a.M = v.n_pad; a.N = v.Cp; a.K = v.kq_pad;
+    a.lda = v.n_pad; a.ldb = v.Cp; a.ldo = v.Cp;
+    a.split_tile = 1 << 30;
+    CUDA_OK(dgemm::launch(a, st));
+    e->launches++;
+    return 0;
+}
+
+static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
+    const View& v = e->v;
+    dgemm::Args a;
+    a.A1 = v.omega; a.A2 = v.kd; a.B = v.ZU; a.Out = v.G;
+    a.M = v.Cp; a.N = v.ldg; a.K = v.n_pad;
+    a.lda = v.Cp; a.ldb = v.ldg; a.ldo = v.ldg;
+    a.split_tile = v.M_pad / dgemm::BN;
+    CUDA_OK(dgemm::launch(a, st));
+    e->launches++;
+    return 0;
+}
+
+static size_t solve_smem_bytes(const View& v) {
+    return ((size_t)v.M + 5 * (size_t)v.pq + MAX_SMALL + SOLVE_THREADS / 32 + 8) * sizeof(double);
+}
+
+static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* ra, double* rb, double* rt, int cap,
+                                cudaStream_t st) {
+    const View& v = e->v;
+    if (launch_gram_gemm(e, st)) return -1;
+    const size_t per = (size_t)v.NV * v.Cp;
+    reduce_partials_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(v);
+    e->launches++;
+    const size_t smem = solve_smem_bytes(v);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    solve_logit_rsr_kernel<<<v.Cp, SOLVE_THREADS, smem, st>>>(v, dbg, ra, rb, rt, cap);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+const char* occu_last_error(void) { return g_err; }
+int occu_abi_version(void) { return OCCU_ABI_VERSION; }
+
+size_t occu_workspace_bytes(const occu_problem_t* prob) {
+    View v;
+    memset(&v, 0, sizeof(v));
+    if (fill_dims(prob, v)) return 0;
+    size_t total = 0;
+    carve(v, nullptr, &total, prob->debug);
+    return total;
+}
+
+int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes, void* stream, occu_engine_t** out) {
+    if (!out) return set_err("null out pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    View v;
+    memset(&v, 0, sizeof(v));
+    if (fill_dims(P, v)) return -1;
+    size_t need = 0;
+    carve(v, nullptr, &need, P->debug);
+    if (!workspace || workspace_bytes < need) return set_err("workspace too small");
+    if ((uintptr_t)workspace % 256) return set_err("workspace must be 256-byte aligned");
+    if (!P->X || !P->K || !P->Qrsr || !P->W || !P->y || !P->visit_ptr || !P->site_class)
+        return set_err("null problem array");
+    if (!P->a_mu || !P->a_prec || !P->b_mu || !P->b_prec) return set_err("null hyper-parameter array");
+    carve(v, (char*)workspace, &need, P->debug);
+
+    occu_engine* e = new (std::nothrow) occu_engine;
+    if (!e) return set_err("out of host memory");
+    e->v = v;
+    e->prob = *P;
+    e->pg_fp64 = P->pg_fp64;
+    e->debug = P->debug;
+    e->launches = 0;
+    e->ws = (char*)workspace;
+    e->ws_bytes = need;
+
+    // hyper-parameters: prec @ mu folded once (base.py:161-162)
+    HParams h;
+    memset(&h, 0, sizeof(h));
+    h.tau_rate = P->tau_rate;
+    h.tau_shape = P->tau_shape;
+    for (int a = 0; a < v.r; a++) {
+        double s = 0.0;
+        for (int b = 0; b < v.r; b++) {
+            h.a_prec[a * v.r + b] = P->a_prec[a * v.r + b];
+            s += P->a_prec[a * v.r + b] * P->a_mu[b];
+        }
+        h.a_pm[a] = s;
+    }
+    for (int a = 0; a < v.p; a++) {
+        double s = 0.0;
+        for (int b = 0; b < v.p; b++) {
+            h.b_prec[a * v.p + b] = P->b_prec[a * v.p + b];
+            s += P->b_prec[a * v.p + b] * P->b_mu[b];
+        }
+        h.b_pm[a] = s;
+    }
+#define FAIL_IF(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) {                                             \
+            delete e;                                                        \
+            return set_err("CUDA error %s at %s", cudaGetErrorString(_e), #call); \
+        }                                                                    \
+    } while (0)
+    FAIL_IF(cudaMemsetAsync(workspace, 0, need, st));
+    FAIL_IF(cudaMemcpyAsync((void*)v.hp, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    FAIL_IF(cudaStreamSynchronize(st));  // h is a stack object
+    FAIL_IF(cudaMemcpyAsync((void*)v.W, P->W, (size_t)v.V * v.r * 8, cudaMemcpyDeviceToDevice, st));
+    FAIL_IF(cudaMemcpyAsync((void*)v.y, P->y, (size_t)v.V, cudaMemcpyDeviceToDevice, st));
+    FAIL_IF(cudaMemcpyAsync((void*)v.visit_ptr, P->visit_ptr, ((size_t)v.n + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    FAIL_IF(cudaMemcpyAsync((void*)v.site_class, P->site_class, (size_t)v.n, cudaMemcpyDeviceToDevice, st));
+    FAIL_IF(cudaMemcpyAsync((void*)v.Qrsr, P->Qrsr, (size_t)v.q * v.q * 8, cudaMemcpyDeviceToDevice, st));
+    build_design_kernel<<<v.n, 128, v.pq * sizeof(double), st>>>(v, P->X, P->K);
+    e->launches++;
+    const size_t total = (size_t)v.n * v.Cp;
+    reset_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
+    set_control_kernel<<<1, 1, 0, st>>>(v.ctl, 0u, 1, -1, 1);
+    e->launches += 2;
+    FAIL_IF(cudaGetLastError());
+#undef FAIL_IF
+    *out = e;
+    return 0;
+}
+
+void occu_destroy(occu_engine_t* eng) { delete eng; }
+
+long long occu_launch_count(const occu_engine_t* eng) { return eng ? eng->launches : 0; }
+
+static int field_info(const occu_engine* e, int field, void** ptr, int* d, int* is_u8) {
+    const View& v = e->v;
+    *is_u8 = 0;
+    switch (field) {
+        case OCCU_F_ALPHA: *ptr = v.alpha; *d = v.r; return 0;
+        case OCCU_F_BETA: *ptr = v.theta; *d = v.p; return 0;
+        case OCCU_F_ETA: *ptr = v.theta + (size_t)v.p * v.Cp; *d = v.q; return 0;
+        case OCCU_F_TAU: *ptr = v.tau; *d = 1; return 0;
+        case OCCU_F_Z: *ptr = v.z; *d = v.n; *is_u8 = 1; return 0;
+        case OCCU_F_OMEGA: *ptr = v.omega; *d = v.n; return 0;
+        case OCCU_F_PSI: *ptr = v.psi; *d = v.n; return 0;
+        case OCCU_F_ZPROB:
+            if (!v.zprob) return set_err("ZPROB needs a debug engine");
+            *ptr = v.zprob; *d = v.n; return 0;
+        default: return set_err("unknown or unsupported field");
+    }
+}
+
+// kd must follow z when z is set from outside
+__global__ void kd_from_z_kernel(View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (size_t)v.n * v.Cp) v.kd[idx] = (double)v.z[idx] - 0.5;
+}
+
+int occu_set_field(occu_engine_t* e, int field, const void* src, void* stream) {
+    if (!e || !src) return set_err("null argument");
+    if (field == OCCU_F_PSI || field == OCCU_F_ZPROB) return set_err("field is read-only");
+    cudaStream_t st = (cudaStream_t)stream;
+    void* ptr; int d, u8;
+    if (field_info(e, field, &ptr, &d, &u8)) return -1;
+    const View& v = e->v;
+    dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
+    if (u8) to_chain_minor_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)src, (uint8_t*)ptr, v.C, v.Cp, d);
+    else to_chain_minor_kernel<double><<<grid, block, 0, st>>>((const double*)src, (double*)ptr, v.C, v.Cp, d);
+    e->launches++;
+    if (field == OCCU_F_Z) {
+        const size_t total = (size_t)v.n * v.Cp;
+        kd_from_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
+        e->launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_get_field(occu_engine_t* e, int field, void* dst, void* stream) {
+    if (!e || !dst) return set_err("null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    void* ptr; int d, u8;
+    if (field_info(e, field, &ptr, &d, &u8)) return -1;
+    const View& v = e->v;
+    dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
+    if (u8) to_chain_major_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)ptr, (uint8_t*)dst, v.C, v.Cp, d);
+    else to_chain_major_kernel<double><<<grid, block, 0, st>>>((const double*)ptr, (double*)dst, v.C, v.Cp, d);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_reset(occu_engine_t* e, void* stream) {
+    if (!e) return set_err("null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const View& v = e->v;
+    const size_t total = (size_t)v.n * v.Cp;
+    reset_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
+    set_control_kernel<<<1, 1, 0, st>>>(v.ctl, 0u, 1, -1, 1);
+    CUDA_OK(cudaMemsetAsync(v.status, 0, (size_t)v.Cp * 4, st));
+    e->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int read_fails(occu_engine* e, cudaStream_t st) {
+    Control h;
+    CUDA_OK(cudaMemcpyAsync(&h, e->v.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return h.fails;
+}
+
+int occu_sweep(occu_engine_t* e, int n_iters, double* rec_alpha, double* rec_beta, double* rec_tau, int rec_start,
+               int rec_capacity, void* stream) {
+    if (!e) return set_err("null engine");
+    if (n_iters < 0) return set_err("n_iters < 0");
+    if (rec_alpha && (!rec_beta || !rec_tau || rec_start < 0 || rec_start + n_iters > rec_capacity))
+        return set_err("bad record buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const View& v = e->v;
+    // rec_index lives on the device so that the iteration body is launch-parameter free
+    {
+        Control h;
+        CUDA_OK(cudaMemcpyAsync(&h, v.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        set_control_kernel<<<1, 1, 0, st>>>(v.ctl, h.iter, h.first, rec_alpha ? rec_start : -1, 0);
+        e->launches++;
+    }
+    SolveDebug dbg;
+    memset(&dbg, 0, sizeof(dbg));
+    for (int it = 0; it < n_iters; it++) {
+        if (launch_psi_gemm(e, st)) return -1;
+        if (e->pg_fp64) launch_site_pass<double>(e, st);
+        else launch_site_pass<float>(e, st);
+        if (launch_gaussian_half(e, dbg, rec_alpha, rec_beta, rec_tau, rec_capacity, st)) return -1;
+        advance_kernel<<<1, 1, 0, st>>>(v.ctl);
+        e->launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return read_fails(e, st);
+}
+
+int occu_debug_gaussian_half(occu_engine_t* e, const double* normals, const double* tau_in, const double* omega_a,
+                             const occu_debug_out_t* out, void* stream) {
+    if (!e) return set_err("null engine");
+    if (!e->debug) return set_err("engine was not created with debug = 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    SolveDebug dbg;
+    memset(&dbg, 0, sizeof(dbg));
+    dbg.normals = normals;
+    dbg.tau_in = tau_in;
+    dbg.enabled = out ? 1 : 0;
+    if (out) dbg.out = *out;
+    if (omega_a) launch_alpha_injected(e, omega_a, st);
+    if (launch_gaussian_half(e, dbg, nullptr, nullptr, nullptr, 0, st)) return -1;
+    return read_fails(e, st);
+}
+
+int occu_debug_site_half(occu_engine_t* e, void* stream) {
+    if (!e) return set_err("null engine");
+    if (!e->debug) return set_err("engine was not created with debug = 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    // force the z-update branch even on a fresh engine
+    Control h;
+    CUDA_OK(cudaMemcpyAsync(&h, e->v.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    set_control_kernel<<<1, 1, 0, st>>>(e->v.ctl, h.iter, 0, -1, 0);
+    e->launches++;
+    if (launch_psi_gemm(e, st)) return -1;
+    if (e->pg_fp64) launch_site_pass<double>(e, st);
+    else launch_site_pass<float>(e, st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int occu_pg1(const double* c, size_t count, uint64_t seed, int fp64, double* out, void* stream) {
+    if (!c || !out) return set_err("null argument");
+    if (!count) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((count + 255) / 256);
+    if (fp64) pg1_kernel<double><<<blocks, 256, 0, st>>>(c, count, seed, out);
+    else pg1_kernel<float><<<blocks, 256, 0, st>>>(c, count, seed, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_truncnorm(const double* loc, const uint8_t* positive, const double* u, size_t count, uint64_t seed, double* out,
+                   void* stream) {
+    if (!loc || !positive || !out) return set_err("null argument");
+    if (!count) return 0;
+    truncnorm_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(loc, positive, u, count, seed, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_gamma(const double* shape, const double* rate, size_t count, uint64_t seed, double* out, void* stream) {
+    if (!shape || !rate || !out) return set_err("null argument");
+    if (!count) return 0;
+    gamma_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(shape, rate, count, seed, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_precision_mvnorm_batched(int d, int count, const double* b, double* P, const double* z, uint64_t seed, double* x,
+                                  void* stream) {
+    if (!b || !P || !x) return set_err("null argument");
+    if (d < 1 || d > 224) return set_err("d must be in [1, 224]");
+    if (count < 1) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = ((size_t)d * (d + 1) / 2 + d) * sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(precision_mvnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int* fails = nullptr;
+    CUDA_OK(cudaMalloc(&fails, sizeof(int)));  // test hook only; the sweep never allocates
+    CUDA_OK(cudaMemsetAsync(fails, 0, sizeof(int), st));
+    precision_mvnorm_kernel<<<count, SOLVE_THREADS, smem, st>>>(d, b, P, z, seed, x, fails);
+    int h = 0;
+    cudaError_t err = cudaMemcpyAsync(&h, fails, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(fails);
+    CUDA_OK(err);
+    if (h) set_err("Cholesky factorization/solver failed!");
+    return h;
+}
+
+int occu_ensure_sums_to_zero_batched(int d, int count, const double* x, const double* z, double* out, void* stream) {
+    if (!x || !z || !out) return set_err("null argument");
+    if (count < 1 || d < 1) return 0;
+    sums_to_zero_kernel<<<count, 32, 0, (cudaStream_t)stream>>>(d, x, z, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_gemm_tn(const double* A, const double* B, double* Out, int M, int N, int K, int lda, int ldb, int ldo,
+                 void* stream) {
+    if (!A || !B || !Out) return set_err("null argument");
+    if (M % dgemm::BM || N % dgemm::BN || K % dgemm::BK) return set_err("M, N must be multiples of 128 and K of 16");
+    dgemm::Args a;
+    a.A1 = a.A2 = A; a.B = B; a.Out = Out;
+    a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldo = ldo;
+    a.split_tile = 1 << 30;
+    CUDA_OK(dgemm::launch(a, (cudaStream_t)stream));
+    return 0;
+}
+
+int occu_chain_summaries(const double* rec, int chains, int draws, int dim, int max_lag, double* out, void* stream) {
+    if (!rec || !out) return set_err("null argument");
+    if (chains < 1 || draws < 2 || dim < 1 || max_lag < 0 || max_lag >= draws) return set_err("bad summary dimensions");
+    chain_summaries_kernel<<<chains * dim, 128, 0, (cudaStream_t)stream>>>(rec, chains, draws, dim, max_lag, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

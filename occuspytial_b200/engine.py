@@ -1,0 +1,193 @@
+"""Thin Python owner of one device engine (one GPU's shard of lock-step chains).
+
+PyTorch is used for exactly three things here: allocating device memory (the engine's workspace,
+the problem arrays, the record buffers), host<->device copies, and the CUDA stream.  All compute
+goes through the C ABI in ``_lib`` (include/occu_b200.h).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_MODEL_IDS = {'logit_rsr': _lib.LOGIT_RSR, 'probit_rsr': _lib.PROBIT_RSR, 'logit_icar': _lib.LOGIT_ICAR}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.EngineError('occuspytial_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch
+
+
+class DeviceEngine:
+    """Engine for ``chains`` lock-step chains of one model on one CUDA device.
+
+    Parameters
+    ----------
+    model : {'logit_rsr', 'probit_rsr', 'logit_icar'}
+    problem : dict
+        Host (NumPy) arrays: X (n, p), W_rows (V, r), y_rows (V,), visit_ptr (n + 1,), site_class (n,),
+        and for RSR models K (n, q), Qrsr (q, q); for ICAR Qband (n, bw + 1); hyper-parameters
+        tau_rate, tau_shape, a_mu, a_prec, b_mu, b_prec.
+    chains, chain_offset, seed : int
+        Number of chains on this device, global id of the first one, Philox key.
+    """
+
+    def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.torch = torch
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.model = model
+        self.chains = int(chains)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        X = np.ascontiguousarray(problem['X'], dtype=np.float64)
+        self.n, self.p = X.shape
+        W_rows = np.ascontiguousarray(problem['W_rows'], dtype=np.float64)
+        self.V, self.r = W_rows.shape
+        self.q = int(problem['K'].shape[1]) if problem.get('K') is not None else 0
+        self.eta_dim = self.q if self.q else self.n
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+            dev = {}
+
+            def up(name, arr, dtype):
+                a = np.ascontiguousarray(arr, dtype=dtype)
+                self.h2d_bytes += a.nbytes
+                t = torch.from_numpy(a).to(self.device, non_blocking=False)
+                dev[name] = t
+                return t.data_ptr()
+
+            P = _lib.Problem()
+            P.abi_version = _lib.ABI_VERSION
+            P.model = _MODEL_IDS[model]
+            P.n, P.p, P.r, P.q, P.V = self.n, self.p, self.r, self.q, self.V
+            P.chains, P.chain_offset = self.chains, int(chain_offset)
+            P.debug, P.pg_fp64 = int(bool(debug)), int(bool(pg_fp64))
+            P.icar_bw = int(problem.get('icar_bw', 0))
+            P.seed = int(seed) & (2**64 - 1)
+            P.X = up('X', X, np.float64)
+            P.K = up('K', problem['K'], np.float64) if self.q else None
+            P.Qrsr = up('Qrsr', problem['Qrsr'], np.float64) if self.q else None
+            P.Qband = up('Qband', problem['Qband'], np.float64) if problem.get('Qband') is not None else None
+            P.W = up('W', W_rows, np.float64)
+            P.y = up('y', problem['y_rows'], np.uint8)
+            P.visit_ptr = up('visit_ptr', problem['visit_ptr'], np.int32)
+            P.site_class = up('site_class', problem['site_class'], np.uint8)
+            P.tau_rate, P.tau_shape = float(problem['tau_rate']), float(problem['tau_shape'])
+            self._host = [np.ascontiguousarray(problem[k], dtype=np.float64) for k in ('a_mu', 'a_prec', 'b_mu', 'b_prec')]
+            P.a_mu, P.a_prec, P.b_mu, P.b_prec = (a.ctypes.data for a in self._host)
+            self._problem = P
+            nbytes = self.lib.occu_workspace_bytes(C.byref(P))
+            if nbytes == 0:
+                _lib.check(-1, 'occu_workspace_bytes')
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self.workspace.data_ptr() + 255) // 256 * 256
+            handle = C.c_void_p()
+            _lib.check(self.lib.occu_create(C.byref(P), base, nbytes, self.stream.cuda_stream, C.byref(handle)),
+                       'occu_create')
+            self.handle = handle
+            self.stream.synchronize()
+            del dev  # the engine copied the problem into its workspace
+
+    # ---- state ---------------------------------------------------------------------------------
+    def _field_shape(self, field):
+        return {_lib.F_ALPHA: (self.r,), _lib.F_BETA: (self.p,), _lib.F_ETA: (self.eta_dim,), _lib.F_TAU: (),
+                _lib.F_Z: (self.n,), _lib.F_OMEGA: (self.n,), _lib.F_PSI: (self.n,), _lib.F_EPS: (self.n,),
+                _lib.F_ZPROB: (self.n,)}[field]
+
+    def set_field(self, field, values):
+        torch = self.torch
+        dtype = np.uint8 if field == _lib.F_Z else np.float64
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=dtype),
+                                                   (self.chains,) + self._field_shape(field)))
+        self.h2d_bytes += arr.nbytes
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            t = torch.from_numpy(arr).to(self.device)
+            _lib.check(self.lib.occu_set_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_set_field')
+            self.stream.synchronize()
+
+    def get_field(self, field):
+        torch = self.torch
+        dtype = torch.uint8 if field == _lib.F_Z else torch.float64
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            t = torch.empty((self.chains,) + self._field_shape(field), dtype=dtype, device=self.device)
+            _lib.check(self.lib.occu_get_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_get_field')
+            self.stream.synchronize()
+            out = t.cpu().numpy()
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def set_start(self, start):
+        """start: dict of chain-major arrays alpha (C, r), beta (C, p), tau (C,), eta (C, q|n)[, eps (C, n)]."""
+        _lib.check(self.lib.occu_reset(self.handle, self.stream.cuda_stream), 'occu_reset')
+        self.set_field(_lib.F_ALPHA, start['alpha'])
+        self.set_field(_lib.F_BETA, start['beta'])
+        self.set_field(_lib.F_TAU, start['tau'])
+        self.set_field(_lib.F_ETA, start['eta'])
+        if self.model == 'probit_rsr':
+            self.set_field(_lib.F_EPS, start['eps'])
+
+    # ---- sampling ------------------------------------------------------------------------------
+    def alloc_record(self, capacity):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            return {
+                'alpha': torch.zeros((self.chains, capacity, self.r), dtype=torch.float64, device=self.device),
+                'beta': torch.zeros((self.chains, capacity, self.p), dtype=torch.float64, device=self.device),
+                'tau': torch.zeros((self.chains, capacity), dtype=torch.float64, device=self.device),
+            }
+
+    def sweep(self, n_iters, record=None, rec_start=0):
+        """Advance every chain by ``n_iters`` iterations; returns the number of failed chains."""
+        if record is None:
+            ra = rb = rt = None
+            cap = 0
+        else:
+            ra, rb, rt = record['alpha'].data_ptr(), record['beta'].data_ptr(), record['tau'].data_ptr()
+            cap = record['tau'].shape[1]
+        with self.torch.cuda.device(self.device):
+            return _lib.check(self.lib.occu_sweep(self.handle, int(n_iters), ra, rb, rt, int(rec_start), int(cap),
+                                                  self.stream.cuda_stream), 'occu_sweep')
+
+    @property
+    def launches(self):
+        return int(self.lib.occu_launch_count(self.handle))
+
+    # ---- deterministic-piece hooks (tests) -------------------------------------------------------
+    def debug_gaussian_half(self, normals=None, tau=None, omega_a=None):
+        torch = self.torch
+        C_, q, p, r = self.chains, self.q, self.p, self.r
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            def dev(a):
+                return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+            tn, tt, to = dev(normals), dev(tau), dev(omega_a)
+            shapes = dict(eta_prec=(C_, q, q), eta_b=(C_, q), eta_chol=(C_, q, q), eta_mean=(C_, q),
+                          beta_prec=(C_, p, p), beta_b=(C_, p), alpha_prec=(C_, r, r), alpha_b=(C_, r), tau_rate=(C_,))
+            bufs = {k: torch.zeros(s, dtype=torch.float64, device=self.device) for k, s in shapes.items()}
+            out = _lib.DebugOut(**{k: t.data_ptr() for k, t in bufs.items()})
+            fails = _lib.check(self.lib.occu_debug_gaussian_half(
+                self.handle, None if tn is None else tn.data_ptr(), None if tt is None else tt.data_ptr(),
+                None if to is None else to.data_ptr(), C.byref(out), self.stream.cuda_stream), 'occu_debug_gaussian_half')
+            self.stream.synchronize()
+            res = {k: t.cpu().numpy() for k, t in bufs.items()}
+        res['fails'] = fails
+        return res
+
+    def debug_site_half(self):
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.occu_debug_site_half(self.handle, self.stream.cuda_stream), 'occu_debug_site_half')
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None:
+            self.lib.occu_destroy(self.handle)
+            self.handle = None
+            self.workspace = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

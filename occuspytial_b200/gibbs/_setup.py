@@ -1,0 +1,116 @@
+"""One-off host-side setup feeding the sweep: site partition, CSR packing, RSR basis, banded ICAR Q.
+
+Replaces the setup half of GibbsBase._configure (base.py:107-152), LogitRSRGibbs._configure_rsr
+(logit.py:415-460) and ProbitRSRGibbs._configure (probit.py:115-148).  Vectorised: the reference's
+``site not in surveyed`` list scans are O(n * n_s) (base.py:125-127) and its Moran operator is a
+dense n x n eigen-problem (logit.py:422-433).
+"""
+import numpy as np
+from scipy import sparse
+from scipy.sparse.linalg import LinearOperator, eigsh
+
+DENSE_LIMIT = 3000  # up to this many sites the reference's dense eigh is reproduced exactly
+
+
+def partition(y_data, n):
+    """Initial z and the obs / not_obs / not_surveyed partition (base.py:113-137), dict order preserved."""
+    surveyed = np.asarray(y_data.surveyed, dtype=np.int64)
+    detected = np.fromiter((bool(np.any(y_data[int(s)])) for s in surveyed), dtype=bool, count=surveyed.size)
+    z = np.ones(n)
+    z[surveyed] = detected
+    mask = np.zeros(n, dtype=bool)
+    mask[surveyed] = True
+    site_class = np.zeros(n, dtype=np.uint8)          # OCCU_SITE_NOT_SURVEYED
+    site_class[surveyed[~detected]] = 1               # OCCU_SITE_NOT_OBS
+    site_class[surveyed[detected]] = 2                # OCCU_SITE_OBS
+    return dict(
+        z=z,
+        site_class=site_class,
+        not_surveyed=np.nonzero(~mask)[0].tolist(),
+        not_obs=surveyed[~detected].tolist(),
+        obs=surveyed[detected].tolist(),
+    )
+
+
+def moran_operator(Q, X):
+    """Return (matvec-able LinearOperator, scale) of n * P A P / sum(A), P = I - X (X'X)^-1 X' (logit.py:417-428)."""
+    Q = sparse.csr_matrix(Q)
+    n = Q.shape[0]
+    A = -Q
+    A = (A - sparse.diags(A.diagonal())).tocsr()
+    A.eliminate_zeros()
+    total = A.sum()
+    XtX_inv = np.linalg.inv(X.T @ X)
+
+    def project(v):
+        return v - X @ (XtX_inv @ (X.T @ v))
+
+    def matvec(v):
+        v = np.asarray(v, dtype=np.float64).reshape(n, -1)
+        return (n / total) * project(A @ project(v))
+
+    return LinearOperator((n, n), matvec=matvec, matmat=matvec, dtype=np.float64), A, XtX_inv
+
+
+def rsr_basis(Q, X, r=0.5, q=None):
+    """RSR basis K (n x q): leading eigenvectors of the Moran operator (logit.py:430-447).
+
+    n <= DENSE_LIMIT: dense ``eigh`` exactly as the reference.  Larger n: Lanczos (``eigsh``, 'LA')
+    on the implicit operator; with only a threshold ``r`` the number of eigenpairs is grown until the
+    smallest one falls below ``r``.
+    """
+    n = X.shape[0]
+    if q is None or not q:
+        if not 0 <= r <= 1:
+            raise ValueError('Threshold value needs to be in [0, 1]')
+    op, A, XtX_inv = moran_operator(Q, X)
+    if n <= DENSE_LIMIT:
+        P = -np.linalg.multi_dot([X, XtX_inv, X.T])
+        P[np.diag_indices_from(P)] += 1
+        omega = n * (P.T @ (A @ P)) / A.sum()
+        w, v = np.linalg.eigh(omega)
+        if q:
+            qq = int(q)
+        else:
+            qq = int(w[w >= r].size)
+            if not qq:
+                raise ValueError('The Moran Operator Matrix of the data has no positive eigenvalues. '
+                                 'Set threshold to a lower value')
+        return np.ascontiguousarray(v[:, -qq:])
+    if q:
+        w, v = eigsh(op, k=int(q), which='LA')
+        order = np.argsort(w)
+        return np.ascontiguousarray(v[:, order])
+    k = min(max(64, n // 16), n - 2)
+    while True:
+        w, v = eigsh(op, k=k, which='LA')
+        order = np.argsort(w)
+        w, v = w[order], v[:, order]
+        if w[0] < r or k >= n - 2:
+            keep = w >= r
+            if not keep.any():
+                raise ValueError('The Moran Operator Matrix of the data has no positive eigenvalues. '
+                                 'Set threshold to a lower value')
+            return np.ascontiguousarray(v[:, keep])
+        k = min(2 * k, n - 2)
+
+
+def verify_singular(Q):
+    """Robust version of GibbsBase._verify_spatial_precision (base.py:166-170).
+
+    The reference's shift-invert ``eigsh(sigma=1e-3, which='SA')`` returns a positive eigenvalue whenever
+    0 < lambda_2 < 1e-3 and then rejects valid ICAR matrices of large lattices.  Here: an exactly
+    row-sum-zero Q is singular by construction; otherwise the eigenvalue nearest to zero is computed.
+    """
+    Qs = sparse.csc_matrix(Q, dtype=np.float64)
+    n = Qs.shape[0]
+    scale = abs(Qs).max() if Qs.nnz else 1.0
+    if np.abs(Qs @ np.ones(n)).max() <= 1e-10 * max(scale, 1.0):
+        return
+    if n <= 2000:
+        lam = np.linalg.eigvalsh(Qs.toarray())
+        smallest = lam[np.argmin(np.abs(lam))]
+    else:
+        smallest = eigsh(Qs, k=1, sigma=-1e-6, which='LM', return_eigenvectors=False)[0]
+    if smallest >= 1e-4:
+        raise ValueError('Spatial precision matrix Q must be singular.')
