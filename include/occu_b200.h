@@ -4,7 +4,7 @@
  * Drop-in boundary: the reference has no FFI of its own; its native layer is two
  * Cython modules (occuspytial/distributions.pyx, occuspytial/data.pyx) called from the pure-Python
  * sweep (occuspytial/gibbs/{base,logit,probit}.py).  This library replaces that whole L2+L1 layer:
- * the Python host (occuspytial_b200/gibbs/*.py) keeps the reference's sampler API and calls the entry
+ * the Python host (occuspytial_b200/gibbs/) keeps the reference's sampler API and calls the entry
  * points below through ctypes.  Each entry point cites the reference interface it replaces.
  *
  * Conventions
@@ -135,6 +135,15 @@ int occu_sweep(occu_engine_t* eng, int n_iters, double* rec_alpha, double* rec_b
 
 /* Number of kernels launched by this engine so far (bench.py's gpu_launches). */
 long long occu_launch_count(const occu_engine_t* eng);
+
+/*
+ * Optional per-kernel-class timing with CUDA events on the engine's stream (bench.py's roofline figures).
+ * Classes: 0 psi GEMM, 1 site pass, 2 Gram GEMM, 3 partial-sum reduction, 4 per-chain solve.
+ * Profiling mode synchronises once per iteration; leave it off for throughput runs.
+ * occu_get_kernel_ms fills accumulated milliseconds and launch counts, returns the number of classes.
+ */
+int occu_set_profiling(occu_engine_t* eng, int on);
+int occu_get_kernel_ms(const occu_engine_t* eng, double* ms, long long* calls, int count);
 
 /* ---- deterministic-piece hooks (parity tests; need prob.debug = 1) ---------------------------- */
 

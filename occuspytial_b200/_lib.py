@@ -48,6 +48,8 @@ SIGNATURES = {
     'occu_reset': (C.c_int, [C.c_void_p, C.c_void_p]),
     'occu_sweep': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'occu_launch_count': (C.c_longlong, [C.c_void_p]),
+    'occu_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
+    'occu_get_kernel_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     'occu_debug_gaussian_half': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DebugOut),
                                            C.c_void_p]),
     'occu_debug_site_half': (C.c_int, [C.c_void_p, C.c_void_p]),

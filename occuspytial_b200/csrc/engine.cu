@@ -91,6 +91,9 @@ struct View {
     Control* ctl;
 };
 
+// kernel classes timed by the optional profiler (occu_set_profiling / occu_get_kernel_ms)
+enum { KC_PSI_GEMM = 0, KC_SITE_PASS = 1, KC_GRAM_GEMM = 2, KC_REDUCE = 3, KC_SOLVE = 4, KC_COUNT = 5 };
+
 struct occu_engine {
     View v;
     occu_problem_t prob;
@@ -98,6 +101,10 @@ struct occu_engine {
     long long launches;
     char* ws;
     size_t ws_bytes;
+    int profiling;
+    double kernel_ms[KC_COUNT];
+    long long kernel_calls[KC_COUNT];
+    cudaEvent_t ev[KC_COUNT + 1];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -871,13 +878,34 @@ static size_t solve_smem_bytes(const View& v) {
     return ((size_t)v.M + 5 * (size_t)v.pq + MAX_SMALL + SOLVE_THREADS / 32 + 8) * sizeof(double);
 }
 
+#define PROF_MARK(e, k, st)                                           \
+    do {                                                              \
+        if ((e)->profiling) cudaEventRecord((e)->ev[k], st);          \
+    } while (0)
+
+// profiling mode synchronises after every iteration to read the event pairs
+static int prof_collect(occu_engine* e, cudaStream_t st) {
+    if (!e->profiling) return 0;
+    CUDA_OK(cudaEventSynchronize(e->ev[KC_COUNT]));
+    for (int k = 0; k < KC_COUNT; k++) {
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, e->ev[k], e->ev[k + 1]));
+        e->kernel_ms[k] += ms;
+        e->kernel_calls[k] += 1;
+    }
+    return 0;
+}
+
 static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* ra, double* rb, double* rt, int cap,
                                 cudaStream_t st) {
     const View& v = e->v;
+    PROF_MARK(e, KC_GRAM_GEMM, st);
     if (launch_gram_gemm(e, st)) return -1;
+    PROF_MARK(e, KC_REDUCE, st);
     const size_t per = (size_t)v.NV * v.Cp;
     reduce_partials_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(v);
     e->launches++;
+    PROF_MARK(e, KC_SOLVE, st);
     const size_t smem = solve_smem_bytes(v);
     static size_t configured = 0;
     if (smem > configured) {
@@ -886,6 +914,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     }
     solve_logit_rsr_kernel<<<v.Cp, SOLVE_THREADS, smem, st>>>(v, dbg, ra, rb, rt, cap);
     e->launches++;
+    PROF_MARK(e, KC_COUNT, st);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -928,6 +957,9 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     e->launches = 0;
     e->ws = (char*)workspace;
     e->ws_bytes = need;
+    e->profiling = 0;
+    for (int k = 0; k < KC_COUNT; k++) { e->kernel_ms[k] = 0.0; e->kernel_calls[k] = 0; }
+    for (int k = 0; k <= KC_COUNT; k++) e->ev[k] = nullptr;
 
     // hyper-parameters: prec @ mu folded once (base.py:161-162)
     HParams h;
@@ -978,7 +1010,27 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     return 0;
 }
 
-void occu_destroy(occu_engine_t* eng) { delete eng; }
+void occu_destroy(occu_engine_t* eng) {
+    if (!eng) return;
+    for (int k = 0; k <= KC_COUNT; k++)
+        if (eng->ev[k]) cudaEventDestroy(eng->ev[k]);
+    delete eng;
+}
+
+int occu_set_profiling(occu_engine_t* e, int on) {
+    if (!e) return set_err("null engine");
+    if (on && !e->ev[0])
+        for (int k = 0; k <= KC_COUNT; k++) CUDA_OK(cudaEventCreate(&e->ev[k]));
+    e->profiling = on ? 1 : 0;
+    for (int k = 0; k < KC_COUNT; k++) { e->kernel_ms[k] = 0.0; e->kernel_calls[k] = 0; }
+    return 0;
+}
+
+int occu_get_kernel_ms(const occu_engine_t* e, double* ms, long long* calls, int count) {
+    if (!e || !ms || !calls) return set_err("null argument");
+    for (int k = 0; k < count && k < KC_COUNT; k++) { ms[k] = e->kernel_ms[k]; calls[k] = e->kernel_calls[k]; }
+    return KC_COUNT;
+}
 
 long long occu_launch_count(const occu_engine_t* eng) { return eng ? eng->launches : 0; }
 
@@ -1079,12 +1131,15 @@ int occu_sweep(occu_engine_t* e, int n_iters, double* rec_alpha, double* rec_bet
     SolveDebug dbg;
     memset(&dbg, 0, sizeof(dbg));
     for (int it = 0; it < n_iters; it++) {
+        PROF_MARK(e, KC_PSI_GEMM, st);
         if (launch_psi_gemm(e, st)) return -1;
+        PROF_MARK(e, KC_SITE_PASS, st);
         if (e->pg_fp64) launch_site_pass<double>(e, st);
         else launch_site_pass<float>(e, st);
         if (launch_gaussian_half(e, dbg, rec_alpha, rec_beta, rec_tau, rec_capacity, st)) return -1;
         advance_kernel<<<1, 1, 0, st>>>(v.ctl);
         e->launches++;
+        if (prof_collect(e, st)) return -1;
     }
     CUDA_OK(cudaGetLastError());
     return read_fails(e, st);

@@ -156,14 +156,30 @@ class DeviceEngine:
     def launches(self):
         return int(self.lib.occu_launch_count(self.handle))
 
+    KERNEL_CLASSES = ('psi_gemm', 'site_pass', 'gram_gemm', 'reduce', 'solve')
+
+    def set_profiling(self, on):
+        _lib.check(self.lib.occu_set_profiling(self.handle, int(bool(on))), 'occu_set_profiling')
+
+    def kernel_ms(self):
+        """{class: (accumulated ms, launches)} since profiling was switched on."""
+        n = len(self.KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        calls = (C.c_longlong * n)()
+        _lib.check(self.lib.occu_get_kernel_ms(self.handle, ms, calls, n), 'occu_get_kernel_ms')
+        return {k: (ms[i], int(calls[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # ---- deterministic-piece hooks (tests) -------------------------------------------------------
     def debug_gaussian_half(self, normals=None, tau=None, omega_a=None):
         torch = self.torch
         C_, q, p, r = self.chains, self.q, self.p, self.r
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            def dev(a):
-                return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
-            tn, tt, to = dev(normals), dev(tau), dev(omega_a)
+            def dev(a, shape):
+                if a is None:
+                    return None
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), shape))
+                return torch.from_numpy(a).to(self.device)
+            tn, tt, to = dev(normals, (C_, q + p + r)), dev(tau, (C_,)), dev(omega_a, (C_, self.V))
             shapes = dict(eta_prec=(C_, q, q), eta_b=(C_, q), eta_chol=(C_, q, q), eta_mean=(C_, q),
                           beta_prec=(C_, p, p), beta_b=(C_, p), alpha_prec=(C_, r, r), alpha_b=(C_, r), tau_rate=(C_,))
             bufs = {k: torch.zeros(s, dtype=torch.float64, device=self.device) for k, s in shapes.items()}
