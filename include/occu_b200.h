@@ -191,7 +191,7 @@ int occu_precision_mvnorm_batched(int d, int count, const double* b, double* P, 
 int occu_ensure_sums_to_zero_batched(int d, int count, const double* x, const double* z, double* out,
                                      void* stream);
 
-/* Out[m][n] = sum_k A[k][m] B[k][n] on the FP64 tensor pipe; M, N multiples of 128, K multiple of 16. */
+/* Out[m][n] = sum_k A[k][m] B[k][n] on the FP64 tensor pipe; M multiple of 128, N of 64, K of 16. */
 int occu_gemm_tn(const double* A, const double* B, double* Out, int M, int N, int K, int lda, int ldb, int ldo,
                  void* stream);
 

@@ -87,6 +87,16 @@ struct RT<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float erfc_(float x) { return erfcf(x); }
     static __device__ __forceinline__ float cospi_(float x) { return cospif(x); }
+    static __device__ __forceinline__ float normcdfinv_(float x) { return normcdfinvf(x); }
+    // four uniforms from exactly one Philox block
+    static __device__ __forceinline__ void unif4(Philox& g, float& a, float& b, float& c, float& d) {
+        g.refill();
+        g.have = 0;
+        a = ((float)(g.buf[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        b = ((float)(g.buf[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        c = ((float)(g.buf[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        d = ((float)(g.buf[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    }
 };
 template <>
 struct RT<double> {
@@ -96,6 +106,15 @@ struct RT<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double erfc_(double x) { return erfc(x); }
     static __device__ __forceinline__ double cospi_(double x) { return cospi(x); }
+    static __device__ __forceinline__ double normcdfinv_(double x) { return normcdfinv(x); }
+    // four 53-bit uniforms from two Philox blocks
+    static __device__ __forceinline__ void unif4(Philox& g, double& a, double& b, double& c, double& d) {
+        g.have = 0;
+        a = g.unif_d();
+        b = g.unif_d();
+        c = g.unif_d();
+        d = g.unif_d();
+    }
 };
 
 // logistic function in FP64, safe for large |x| (scipy.special.expit semantics)

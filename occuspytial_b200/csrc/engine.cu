@@ -66,7 +66,7 @@ struct HParams {
 // device view of an engine (passed to kernels by value)
 struct View {
     int model, n, p, r, q, pq, V, C, Cp, chain_offset;
-    int n_pad, kq_pad, M, M_pad, ldg, n_tiles, NV;
+    int n_pad, kq_pad, M, M_pad, ldz, ldh, ksplit, n_tiles, NV;
     uint64_t seed;
     const double* W;
     const uint8_t* y;
@@ -75,7 +75,7 @@ struct View {
     const double* Qrsr;
     const HParams* hp;
     double* UT;     // [kq_pad][n_pad]
-    double* ZU;     // [n_pad][ldg]   Z | U
+    double* ZU;     // [n_pad][ldz]   Z (M_pad columns) | U (ldh columns)
     double* theta;  // [kq_pad][Cp]   beta rows then eta rows
     double* alpha;  // [r][Cp]
     double* tau;    // [Cp]
@@ -83,7 +83,8 @@ struct View {
     double* omega;  // [n_pad][Cp]
     double* kd;     // [n_pad][Cp]
     uint8_t* z;     // [n][Cp]
-    double* G;      // [Cp][ldg]
+    double* G;      // [Cp][M_pad]    packed joint Gram per chain
+    double* Hpart;  // [ksplit][Cp][ldh]  K-split partials of U'(z - 1/2)
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
     double* zprob;  // [n][Cp] or NULL
@@ -140,7 +141,9 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     v.kq_pad = round_up(v.pq, dgemm::BK);
     v.M = v.pq * (v.pq + 1) / 2;
     v.M_pad = round_up(v.M, dgemm::BN);
-    v.ldg = v.M_pad + round_up(v.pq, dgemm::BN);
+    v.ldh = round_up(v.pq, dgemm::BN);
+    v.ldz = v.M_pad + v.ldh;
+    v.ksplit = (v.n_pad / dgemm::BK >= 64) ? 8 : 1;
     v.n_tiles = (P->n + SITE_TILE - 1) / SITE_TILE;
     v.NV = P->r * (P->r + 1) / 2 + P->r;
     // solve kernel keeps the packed joint Gram + H + a few vectors in shared memory
@@ -160,7 +163,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.site_class = c.take<uint8_t>(v.n);
     v.Qrsr = c.take<double>((size_t)v.q * v.q);
     v.UT = c.take<double>((size_t)v.kq_pad * v.n_pad);
-    v.ZU = c.take<double>((size_t)v.n_pad * v.ldg);
+    v.ZU = c.take<double>((size_t)v.n_pad * v.ldz);
     v.theta = c.take<double>((size_t)v.kq_pad * Cp);
     v.alpha = c.take<double>((size_t)v.r * Cp);
     v.tau = c.take<double>(Cp);
@@ -168,7 +171,8 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.omega = c.take<double>((size_t)v.n_pad * Cp);
     v.kd = c.take<double>((size_t)v.n_pad * Cp);
     v.z = c.take<uint8_t>((size_t)v.n * Cp);
-    v.G = c.take<double>(Cp * (size_t)v.ldg);
+    v.G = c.take<double>(Cp * (size_t)v.M_pad);
+    v.Hpart = c.take<double>((size_t)v.ksplit * Cp * v.ldh);
     v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
     v.asum = c.take<double>((size_t)v.NV * Cp);
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
@@ -188,14 +192,14 @@ __global__ void build_design_kernel(View v, const double* __restrict__ X, const 
     __syncthreads();
     for (int a = threadIdx.x; a < v.pq; a += blockDim.x) {
         v.UT[(size_t)a * v.n_pad + i] = u[a];
-        v.ZU[(size_t)i * v.ldg + v.M_pad + a] = u[a];
+        v.ZU[(size_t)i * v.ldz + v.M_pad + a] = u[a];
     }
     for (int m = threadIdx.x; m < v.M; m += blockDim.x) {
         int a = (int)((sqrtf(8.0f * (float)m + 1.0f) - 1.0f) * 0.5f);
         while (a * (a + 1) / 2 > m) a--;
         while ((a + 1) * (a + 2) / 2 <= m) a++;
         const int b = m - a * (a + 1) / 2;
-        v.ZU[(size_t)i * v.ldg + m] = u[a] * u[b];
+        v.ZU[(size_t)i * v.ldz + m] = u[a] * u[b];
     }
 }
 
@@ -256,11 +260,24 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // site pass (logit): z-update, omega_a draws + alpha partial sums, omega_b draw
+//
+// CTA = 128 chains x SITE_TILE sites, thread = chain.
+//  phase 1 (lock-step over the tile's sites, coalesced): z | psi, alpha in FP64; z, kd written; psi kept
+//          in shared memory as the PG argument; z bits kept in a register.
+//  phase 2 (lanes desynchronise): every lane walks its OWN stream of PG draws -- for each site the visits
+//          of an occupied surveyed site (omega_a) and then the site itself (omega_b) -- running one
+//          rejection round per loop trip (pg1_round).  An accepted lane commits and immediately fetches
+//          its next draw, a rejected lane retries: no lane waits for another lane's rejection loop.
+//  phase 3: omega_b (staged in the lane's own shared-memory column) is written out coalesced.
+// Philox streams are keyed by (chain, visit row | site, iteration, stage), so the result does not
+// depend on how lanes interleave.
 // ------------------------------------------------------------------------------------------------
 template <int R, typename PGT>
 __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
-    const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
+    __shared__ PGT arg_s[SITE_TILE][CHAIN_TILE];  // column tid is private to thread tid
+    const int tid = threadIdx.x;
+    const int c = blockIdx.y * CHAIN_TILE + tid;
     const int tile = blockIdx.x;
     const int i0 = tile * SITE_TILE;
     const int i1 = min(i0 + SITE_TILE, v.n);
@@ -272,15 +289,13 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
     double al[R];
 #pragma unroll
     for (int k = 0; k < R; k++) al[k] = v.alpha[(size_t)k * Cp + c];
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
+    // ---- phase 1: z | . ----
+    uint32_t zbits = 0u;
     for (int i = i0; i < i1; i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
         const double psi = v.psi[off];
-        const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
         int zc;
         if (first) {
             zc = v.z[off];
@@ -291,7 +306,8 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
                 double pr = expit_d(psi);  // logit.py:241 / 249
                 if (cls == OCCU_SITE_NOT_OBS) {
                     double prod = 1.0;  // logit.py:242-243: prod_j expit(-w_ij alpha)
-                    for (int vv = v0; vv < v1; vv++) {
+                    const int v1 = v.visit_ptr[i + 1];
+                    for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
                         double lin = 0.0;
 #pragma unroll
                         for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
@@ -308,34 +324,80 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
             v.z[off] = (uint8_t)zc;
             v.kd[off] = (double)zc - 0.5;  // logit.py:252
         }
-        if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
-            // omega_a ~ PG(1, w_ij alpha) over the visits of occupied surveyed sites (logit.py:187-193)
-            for (int vv = v0; vv < v1; vv++) {
-                double w[R];
-                double lin = 0.0;
+        zbits |= (uint32_t)zc << (i - i0);
+        arg_s[i - i0][tid] = (PGT)psi;
+    }
+
+    // ---- phase 2: per-lane stream of PG draws ----
+    double acc[NV];
 #pragma unroll
-                for (int k = 0; k < R; k++) {
-                    w[k] = v.W[(size_t)vv * R + k];
-                    lin += w[k] * al[k];
+    for (int k = 0; k < NV; k++) acc[k] = 0.0;
+    int i = i0 - 1, vv = 0, vend = 0, cur = 0;
+    bool site_pending = false, active = true, have = false, is_visit = false;
+    PGTask<PGT> task;
+    Philox g;
+    while (__any_sync(0xffffffffu, active || have)) {
+        if (!have && active) {
+            for (;;) {
+                if (vv < vend) {  // omega_a ~ PG(1, w_ij alpha) (logit.py:187-193)
+                    cur = vv++;
+                    double lin = 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; k++) lin += v.W[(size_t)cur * R + k] * al[k];
+                    is_visit = true;
+                    g.init(v.seed, gc, (uint32_t)cur, iter, ST_OMEGA_A);
+                    pg1_setup<PGT>((PGT)lin, task);
+                    have = true;
+                    break;
                 }
-                Philox g;
-                g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
-                const double om = (double)pg1_draw<PGT>((PGT)lin, g);
-                const double yk = (double)v.y[vv] - 0.5;
-                int idx = 0;
-#pragma unroll
-                for (int a = 0; a < R; a++) {
-#pragma unroll
-                    for (int b = 0; b <= a; b++) acc[idx++] += om * w[a] * w[b];  // logit.py:222
+                if (site_pending) {  // omega_b ~ PG(1, psi) (logit.py:201-204)
+                    site_pending = false;
+                    cur = i;
+                    is_visit = false;
+                    g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
+                    pg1_setup<PGT>(arg_s[i - i0][tid], task);
+                    have = true;
+                    break;
                 }
-#pragma unroll
-                for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;  // logit.py:223
+                if (++i >= i1) {
+                    active = false;
+                    break;
+                }
+                site_pending = true;
+                if (v.site_class[i] != OCCU_SITE_NOT_SURVEYED && ((zbits >> (i - i0)) & 1u)) {
+                    vv = v.visit_ptr[i];
+                    vend = v.visit_ptr[i + 1];
+                }
             }
         }
-        Philox g;
-        g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
-        v.omega[off] = (double)pg1_draw<PGT>((PGT)psi, g);  // logit.py:201-204
+        if (have) {
+            PGT ub, ux, u3, us, x;
+            RT<PGT>::unif4(g, ub, ux, u3, us);
+            if (pg1_round<PGT>(task, ub, ux, u3, us, x)) {
+                have = false;
+                const double om = 0.25 * (double)x;
+                if (is_visit) {
+                    double w[R];
+#pragma unroll
+                    for (int k = 0; k < R; k++) w[k] = v.W[(size_t)cur * R + k];
+                    const double yk = (double)v.y[cur] - 0.5;
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < R; a++) {
+#pragma unroll
+                        for (int b = 0; b <= a; b++) acc[idx++] += om * w[a] * w[b];  // logit.py:222
+                    }
+#pragma unroll
+                    for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;  // logit.py:223
+                } else {
+                    arg_s[cur - i0][tid] = (PGT)om;
+                }
+            }
+        }
     }
+
+    // ---- phase 3: coalesced write-out ----
+    for (int ii = i0; ii < i1; ii++) v.omega[(size_t)ii * Cp + c] = (double)arg_s[ii - i0][tid];
 #pragma unroll
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
 }
@@ -479,10 +541,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     const uint32_t gc = (uint32_t)(v.chain_offset + c);
     const int cr = c % v.C;  // chain whose injected values a padded chain replicates
 
-    const double* Grow = v.G + (size_t)c * v.ldg;
+    const double* Grow = v.G + (size_t)c * v.M_pad;
     for (int m = tid; m < M; m += T) Gs[m] = Grow[m];
     for (int a = tid; a < pq; a += T) {
-        h[a] = Grow[v.M_pad + a];
+        double hs = 0.0;  // K-split partials, fixed order
+        for (int s = 0; s < v.ksplit; s++) hs += v.Hpart[((size_t)s * Cp + c) * v.ldh + a];
+        h[a] = hs;
         th[a] = v.theta[(size_t)a * Cp + c];
     }
     // normals: eta (q), beta (p), alpha (r)
@@ -853,10 +917,10 @@ static void launch_alpha_injected(occu_engine* e, const double* omega_a, cudaStr
 static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dgemm::Args a;
-    a.A1 = a.A2 = v.UT; a.B = v.theta; a.Out = v.psi;
+    memset(&a, 0, sizeof(a));
+    a.A1 = v.UT; a.B = v.theta; a.Out = v.psi;
     a.M = v.n_pad; a.N = v.Cp; a.K = v.kq_pad;
     a.lda = v.n_pad; a.ldb = v.Cp; a.ldo = v.Cp;
-    a.split_tile = 1 << 30;
     CUDA_OK(dgemm::launch(a, st));
     e->launches++;
     return 0;
@@ -865,10 +929,11 @@ static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
 static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dgemm::Args a;
-    a.A1 = v.omega; a.A2 = v.kd; a.B = v.ZU; a.Out = v.G;
-    a.M = v.Cp; a.N = v.ldg; a.K = v.n_pad;
-    a.lda = v.Cp; a.ldb = v.ldg; a.ldo = v.ldg;
-    a.split_tile = v.M_pad / dgemm::BN;
+    memset(&a, 0, sizeof(a));
+    a.A1 = v.omega; a.B = v.ZU; a.Out = v.G;
+    a.M = v.Cp; a.N = v.M_pad; a.K = v.n_pad;
+    a.lda = v.Cp; a.ldb = v.ldz; a.ldo = v.M_pad;
+    a.A2 = v.kd; a.Out2 = v.Hpart; a.N2 = v.ldh; a.col2 = v.M_pad; a.ldo2 = v.ldh; a.ksplit = v.ksplit;
     CUDA_OK(dgemm::launch(a, st));
     e->launches++;
     return 0;
@@ -1239,11 +1304,12 @@ int occu_ensure_sums_to_zero_batched(int d, int count, const double* x, const do
 int occu_gemm_tn(const double* A, const double* B, double* Out, int M, int N, int K, int lda, int ldb, int ldo,
                  void* stream) {
     if (!A || !B || !Out) return set_err("null argument");
-    if (M % dgemm::BM || N % dgemm::BN || K % dgemm::BK) return set_err("M, N must be multiples of 128 and K of 16");
+    if (M % dgemm::BM || N % dgemm::BN || K % dgemm::BK)
+        return set_err("M must be a multiple of 128, N of 64 and K of 16");
     dgemm::Args a;
-    a.A1 = a.A2 = A; a.B = B; a.Out = Out;
+    memset(&a, 0, sizeof(a));
+    a.A1 = A; a.B = B; a.Out = Out;
     a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldo = ldo;
-    a.split_tile = 1 << 30;
     CUDA_OK(dgemm::launch(a, (cudaStream_t)stream));
     return 0;
 }

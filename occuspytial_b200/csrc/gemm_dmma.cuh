@@ -6,13 +6,17 @@
 //   psi   [n  x C ] = U'[pq x n]'  theta[pq x C]     (X beta + K eta;   logit.py:201, 485)
 //   G     [C  x M ] = Omega[n x C]' Z[n x M]         (vech of [X K]' diag(omega_b) [X K]; logit.py:230, 327-335)
 //   H     [C  x pq] = kd[n x C]'    U[n x pq]        ([X K]' (z - 1/2);             logit.py:231, 481)
-// G and H are produced by ONE launch: column tiles >= split_tile read A from A2 instead of A1.
+// G and H come from ONE launch.  Work items are ordered big-first: all full-K tiles of G, then the few
+// H tiles split `ksplit` ways along K (partials summed in fixed order by the consumer).  The hardware
+// dispatches CTAs in blockIdx order, so the small split items back-fill the last, partially filled wave:
+// with 128 x 64 tiles and 2 CTAs/SM the headline shape (C = 4096, M = 2278 + 67, 148 SMs) runs 4.1 waves of
+// work in 4.125 wave-times instead of 5.
 //
 // FP64 has no tcgen05 / wgmma kind on sm_100a; the FP64 tensor path is mma.sync m8n8k4 (SASS DMMA.8x8x4).
 // Operands are staged global -> shared with a 4-deep cp.async pipeline; rows are padded by 4 doubles so
 // that the per-thread fragment loads (lane = 4*row + k) are bank-conflict free.
 //
-// All extents must be multiples of the tile: M % 128 == 0, N % 128 == 0, K % 16 == 0 (the engine pads
+// All extents must be multiples of the tile: M % 128 == 0, N % 64 == 0, K % 16 == 0 (the engine pads
 // and zero-fills).
 #pragma once
 #include <cuda_runtime.h>
@@ -20,10 +24,13 @@
 
 namespace dgemm {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
-constexpr int LDS = BM + 4;  // padded row length (doubles) of a staged tile
-constexpr int STAGE_DOUBLES = 2 * BK * LDS;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4, THREADS = 256;
+constexpr int WARPS_M = 4, WARPS_N = 2;            // 8 warps, warp tile 32 x 32
+constexpr int MI = BM / WARPS_M / 8, NI = BN / WARPS_N / 8;
+constexpr int LDA_S = BM + 4, LDB_S = BN + 4;      // padded row lengths (doubles): (ld mod 16) == 4
+constexpr int STAGE_DOUBLES = BK * (LDA_S + LDB_S);
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+constexpr int CTAS_PER_SM = 2;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -42,44 +49,79 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 struct Args {
+    // main product: Out[M][N] = A1' B[:, 0:N]
     const double* A1;  // [K][lda]
-    const double* A2;  // [K][lda], used by column tiles >= split_tile (may equal A1)
     const double* B;   // [K][ldb]
     double* Out;       // [M][ldo]
     int M, N, K;
     int lda, ldb, ldo;
-    int split_tile;  // first column tile that reads A2
+    // optional second product, split along K: Out2[s][M][ldo2] = A2[Ks]' B[Ks, col2 : col2 + N2]
+    const double* A2;  // [K][lda] or nullptr
+    double* Out2;      // [ksplit][M][ldo2]
+    int N2, col2, ldo2, ksplit;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_tn_kernel(const Args g) {
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM) gemm_tn_kernel(const Args g) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
-    const double* __restrict__ A = (tile_n >= g.split_tile) ? g.A2 : g.A1;
-    const double* __restrict__ B = g.B;
-    const int KT = g.K / BK;
+    const int tiles_n = g.N / BN;
+    const int main_items = (g.M / BM) * tiles_n;
+    const int KT_all = g.K / BK;
 
-    // 8 warps: 2 along M (64 rows each) x 4 along N (32 cols each)
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const double* __restrict__ A;
+    const double* __restrict__ B;
+    double* __restrict__ Out;
+    int m0, ldo, kt0, kt1;
+    int item = blockIdx.x;
+    if (item < main_items) {
+        const int tile_n = item % tiles_n, tile_m = item / tiles_n;
+        m0 = tile_m * BM;
+        A = g.A1 + m0;
+        B = g.B + tile_n * BN;
+        Out = g.Out + (size_t)m0 * g.ldo + tile_n * BN;
+        ldo = g.ldo;
+        kt0 = 0;
+        kt1 = KT_all;
+    } else {
+        item -= main_items;
+        const int tiles_n2 = g.N2 / BN;
+        const int s = item % g.ksplit;
+        const int tile_n = (item / g.ksplit) % tiles_n2, tile_m = item / (g.ksplit * tiles_n2);
+        const int per = (KT_all + g.ksplit - 1) / g.ksplit;
+        m0 = tile_m * BM;
+        A = g.A2 + m0;
+        B = g.B + g.col2 + tile_n * BN;
+        Out = g.Out2 + ((size_t)s * g.M + m0) * g.ldo2 + tile_n * BN;
+        ldo = g.ldo2;
+        kt0 = min(s * per, KT_all);
+        kt1 = min(kt0 + per, KT_all);
+    }
+    const int KT = kt1 - kt0;
+
+    const int wm = (warp % WARPS_M) * (BM / WARPS_M), wn = (warp / WARPS_M) * (BN / WARPS_N);
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
 
-    double acc[8][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto load_stage = [&](int kt, int slot) {
         double* As = smem + slot * STAGE_DOUBLES;
-        double* Bs = As + BK * LDS;
-        const int k0 = kt * BK;
+        double* Bs = As + BK * LDA_S;
+        const size_t k0 = (size_t)(kt0 + kt) * BK;
 #pragma unroll
-        for (int i = 0; i < (BK * BM / 2) / THREADS; i++) {  // 16-byte chunks
+        for (int i = 0; i < (BK * BM / 2) / THREADS; i++) {  // 16-byte chunks of the A tile
             const int ch = tid + i * THREADS;
             const int r = ch / (BM / 2), c2 = (ch % (BM / 2)) * 2;
-            cp_async16(As + r * LDS + c2, A + (size_t)(k0 + r) * g.lda + m0 + c2);
-            cp_async16(Bs + r * LDS + c2, B + (size_t)(k0 + r) * g.ldb + n0 + c2);
+            cp_async16(As + r * LDA_S + c2, A + (k0 + r) * g.lda + c2);
+        }
+#pragma unroll
+        for (int i = 0; i < (BK * BN / 2) / THREADS; i++) {  // B tile
+            const int ch = tid + i * THREADS;
+            const int r = ch / (BN / 2), c2 = (ch % (BN / 2)) * 2;
+            cp_async16(Bs + r * LDB_S + c2, B + (k0 + r) * g.ldb + c2);
         }
     };
 
@@ -98,29 +140,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tn_kernel(const Args g) {
             cp_async_commit();
         }
         const double* As = smem + (kt % STAGES) * STAGE_DOUBLES;
-        const double* Bs = As + BK * LDS;
+        const double* Bs = As + BK * LDA_S;
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 4) {
-            double af[8], bf[4];
+            double af[MI], bf[NI];
 #pragma unroll
-            for (int i = 0; i < 8; i++) af[i] = As[(ks + fk) * LDS + wm + i * 8 + fr];
+            for (int i = 0; i < MI; i++) af[i] = As[(ks + fk) * LDA_S + wm + i * 8 + fr];
 #pragma unroll
-            for (int j = 0; j < 4; j++) bf[j] = Bs[(ks + fk) * LDS + wn + j * 8 + fr];
+            for (int j = 0; j < NI; j++) bf[j] = Bs[(ks + fk) * LDB_S + wn + j * 8 + fr];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < MI; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
 
     // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) -> 16-byte stores
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int row = m0 + wm + i * 8 + fr;
-        double* orow = g.Out + (size_t)row * g.ldo + n0 + wn + 2 * fk;
+    for (int i = 0; i < MI; i++) {
+        double* orow = Out + (size_t)(wm + i * 8 + fr) * ldo + wn + 2 * fk;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NI; j++) {
             *reinterpret_cast<double2*>(orow + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
     }
@@ -133,8 +174,9 @@ inline cudaError_t launch(const Args& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid(a.N / BN, a.M / BM);
-    gemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a);
+    int items = (a.M / BM) * (a.N / BN);
+    if (a.A2 && a.ksplit > 0) items += (a.M / BM) * (a.N2 / BN) * a.ksplit;
+    gemm_tn_kernel<<<items, THREADS, SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -11,70 +11,99 @@
 
 #define PG_TRUNC 0.64  // truncation point t between the two series representations
 
-// T = float: transcendental work in FP32 (the draw is a random variate, not a deterministic quantity;
-// the KS / moment tests in tests/test_gpu_samplers.py arbitrate).  T = double: validation build.
+// ---------------------------------------------------------------------------------------------
+// PG(1, c) = J*(1, c/2) / 4 by Devroye's alternating-series method, arranged for SIMT execution.
+//
+// The textbook algorithm (Polson-Scott-Windle Alg. 1, as in polyagamma) nests three data-dependent
+// loops: the outer accept loop, the truncated inverse-Gaussian sub-sampler and its own rejection loops.
+// On a GPU that serialises lanes.  Here the sampler is flattened into i.i.d. ROUNDS with no inner loop:
+// every round proposes X from an envelope g >= f and accepts or rejects; a rejected lane simply runs
+// another round, an accepted lane is refilled with its next draw by the caller (site pass), so the
+// lanes of a warp stay busy ("compaction by refill").  With z = |c|/2, K = pi^2/8 + z^2/2, t = 0.64:
+//   right piece  x > t : g = (pi/2) exp(-K x),                    mass p  = (pi / 2K) exp(-K t),  X = t + Exp(1)/K
+//   left, z t < 1      : g = a_0(x) (Levy(1) density x 2),          mass q' = 4 Phi(-1/sqrt t),     X = 1 / Y^2, Y ~ N(0,1) | |Y| > 1/sqrt t,
+//                        pre-accept with probability exp(-z^2 X / 2)
+//   left, z t >= 1     : g = a_0(x) exp(-z^2 x / 2) on (0, inf),    mass q''= 2 exp(-z),            X ~ IG(1/z, 1) (Michael-Schucany-Haas),
+//                        pre-accept iff X <= t
+// followed by the alternating-series squeeze on the ratios r_n = a_n(x)/a_0(x) = (2n+1) exp(-n(n+1) e),
+// e = 2/x (x <= t) or pi^2 x/2 (x > t).  Restarting from the mixture choice after any rejection keeps the
+// accepted draw exactly J*(1, z) distributed because each round is an independent rejection trial against
+// the same envelope.  One round consumes exactly one Philox block (4 uniforms).
+// ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ T pg1_draw(T c, Philox& g) {
+struct PGTask {
+    T K, p_right, mu, hz2;
+    bool small_z;
+};
+
+template <typename T>
+__device__ __forceinline__ void pg1_setup(T c, PGTask<T>& s) {
     typedef RT<T> R;
     const T t = (T)PG_TRUNC;
     const T z = (T)0.5 * fabs(c);
-    const T K = (T)(OCCU_PI * OCCU_PI / 8.0) + (T)0.5 * z * z;
-    // mixture weight of the right (exponential) piece: p / (p + q), evaluated through q / p in log space
-    const T x0 = R::log_(K) + K * t;
-    const T rs = (T)1.25;  // sqrt(1 / t)
-    const T la = R::log_((T)0.5 * R::erfc_(-rs * (t * z - (T)1) * (T)0.70710678118654752)) ;
-    const T lb = R::log_((T)0.5 * R::erfc_(rs * (t * z + (T)1) * (T)0.70710678118654752));
-    const T qdivp = (T)(4.0 / OCCU_PI) * (R::exp_(x0 - z + la) + R::exp_(x0 + z + lb));
-    const T p_right = (T)1 / ((T)1 + qdivp);
-    const bool small_z = z * t < (T)1;  // 1/z > t: truncated IG by the exponential-pair rejection
-    const T mu = small_z ? (T)0 : (T)1 / z;
-    const T hz2 = (T)0.5 * z * z;
+    s.hz2 = (T)0.5 * z * z;
+    s.K = (T)(OCCU_PI * OCCU_PI / 8.0) + s.hz2;
+    s.small_z = z * t < (T)1;
+    s.mu = s.small_z ? (T)1 : (T)1 / z;
+    // q/p with q = q' (small z) or q'' (large z); exp may overflow to inf for huge z => p_right = 0
+    const T two_k_over_pi = s.K * (T)(2.0 / OCCU_PI);
+    const T qdivp = s.small_z ? (T)0.42259909466742100 * two_k_over_pi * R::exp_(s.K * t)  // 4 Phi(-1.25)
+                              : (T)2 * two_k_over_pi * R::exp_(s.K * t - z);
+    s.p_right = (T)1 / ((T)1 + qdivp);
+}
 
-    for (;;) {
-        T x;
-        if (R::unif(g) < p_right) {
-            x = t - R::log_(R::unif(g)) / K;
-        } else if (small_z) {
-            for (;;) {
-                T e1, e2;
-                do {
-                    e1 = -R::log_(R::unif(g));
-                    e2 = -R::log_(R::unif(g));
-                } while (e1 * e1 * t > (T)2 * e2);
-                x = (T)1 + t * e1;
-                x = t / (x * x);
-                if (R::unif(g) <= R::exp_(-hz2 * x)) break;
+// One rejection round.  u[0..3]: uniforms on (0,1).  Returns true and the J*(1,z) variate in x on acceptance.
+template <typename T>
+__device__ __forceinline__ bool pg1_round(const PGTask<T>& s, T ub, T ux, T u3, T us, T& x) {
+    typedef RT<T> R;
+    const T t = (T)PG_TRUNC;
+    bool pre;
+    if (ub < s.p_right) {
+        x = t - R::log_(ux) / s.K;
+        pre = true;
+    } else {
+        const T y = R::normcdfinv_(s.small_z ? ux * (T)0.10564977366685525 : ux);  // Phi(-1.25)
+        const T y2 = y * y;
+        if (s.small_z) {
+            x = (T)1 / y2;
+            pre = (x <= t) && (u3 <= R::exp_(-s.hz2 * x));
+        } else {
+            const T w = s.mu * y2;
+            x = s.mu / ((T)1 + (T)0.5 * w + R::sqrt_(w + (T)0.25 * w * w));  // cancellation-free small root
+            if (u3 * (s.mu + x) > s.mu) x = s.mu * s.mu / x;
+            pre = x <= t;
+        }
+    }
+    const T e = (x > t) ? (T)(OCCU_PI * OCCU_PI * 0.5) * x : (T)2 / x;
+    T sum = (T)1;
+    bool acc = false;
+    for (int n = 1;; n++) {
+        const T rn = (T)(2 * n + 1) * R::exp_(-(T)(n * (n + 1)) * e);
+        if (n & 1) {
+            sum -= rn;
+            if (us <= sum) {
+                acc = true;
+                break;
             }
         } else {
-            do {
-                // IG(mu, 1) by Michael-Schucany-Haas; the small root is written in the cancellation-free form
-                const T u1 = R::unif(g), u2 = R::unif(g);
-                const T nrm = R::sqrt_((T)-2 * R::log_(u1)) * R::cospi_((T)2 * u2);
-                const T w = mu * nrm * nrm;
-                x = mu / ((T)1 + (T)0.5 * w + R::sqrt_(w + (T)0.25 * w * w));
-                if (R::unif(g) * (mu + x) > mu) x = mu * mu / x;
-            } while (x > t);
+            sum += rn;
+            if (us > sum) break;
         }
-        // alternating-series squeeze on the ratios r_n = a_n(x) / a_0(x) = (2n+1) exp(-n(n+1) e), with
-        // e = 2/x (x <= t) or pi^2 x / 2 (x > t); accept when U <= partial sum after an odd term.
-        const T e = (x > t) ? (T)(OCCU_PI * OCCU_PI * 0.5) * x : (T)2 / x;
-        const T u = R::unif(g);
-        T s = (T)1;
-        bool accepted = false;
-        for (int n = 1;; n++) {
-            const T rn = (T)(2 * n + 1) * R::exp_(-(T)(n * (n + 1)) * e);
-            if (n & 1) {
-                s -= rn;
-                if (u <= s) {
-                    accepted = true;
-                    break;
-                }
-            } else {
-                s += rn;
-                if (u > s) break;
-            }
-        }
-        if (accepted) return (T)0.25 * x;
+    }
+    return pre && acc;
+}
+
+// T = float: transcendental work in FP32 (the draw is a random variate, not a deterministic quantity;
+// the KS / moment tests in tests/test_gpu_primitives.py arbitrate).  T = double: validation build.
+template <typename T>
+__device__ __forceinline__ T pg1_draw(T c, Philox& g) {
+    typedef RT<T> R;
+    PGTask<T> s;
+    pg1_setup<T>(c, s);
+    for (;;) {
+        T ub, ux, u3, us, x;
+        R::unif4(g, ub, ux, u3, us);
+        if (pg1_round<T>(s, ub, ux, u3, us, x)) return (T)0.25 * x;
     }
 }
 
