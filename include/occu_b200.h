@@ -160,9 +160,16 @@ int occu_get_kernel_ms(const occu_engine_t* eng, double* ms, long long* calls, i
 int occu_debug_gaussian_half(occu_engine_t* eng, const double* normals, const double* tau_in,
                              const double* omega_a, const occu_debug_out_t* out, void* stream);
 
-/* Run psi = X beta + K eta and the z-update half (logit.py:234-252 / probit.py:245-260); afterwards
- * OCCU_F_ZPROB holds the occupancy probabilities and OCCU_F_Z the new draw. */
-int occu_debug_site_half(occu_engine_t* eng, void* stream);
+/*
+ * Run psi = X beta + K eta and the site half of one iteration: the z-update (logit.py:234-252 /
+ * probit.py:245-260) unless keep_z != 0, the omega_a / omega_b draws and -- probit -- the eps update.
+ * Afterwards OCCU_F_ZPROB holds the occupancy probabilities (keep_z == 0), OCCU_F_Z / OCCU_F_OMEGA /
+ * OCCU_F_EPS the new draws.  Probit only, chain-major, NULL = Philox: u_site [chains][n] and u_visit
+ * [chains][V] inject the uniforms of the reference's inverse-CDF truncated normals (probit.py:190-194,
+ * 205-209), nrm_eps [chains][n] the normals of _update_eps (probit.py:220).
+ */
+int occu_debug_site_half(occu_engine_t* eng, int keep_z, const double* u_site, const double* u_visit,
+                         const double* nrm_eps, void* stream);
 
 /* ---- stand-alone batched primitives ----------------------------------------------------------- */
 

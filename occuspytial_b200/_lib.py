@@ -52,7 +52,7 @@ SIGNATURES = {
     'occu_get_kernel_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     'occu_debug_gaussian_half': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DebugOut),
                                            C.c_void_p]),
-    'occu_debug_site_half': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'occu_debug_site_half': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'occu_pg1': (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_truncnorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p]),
     'occu_gamma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -88,6 +88,8 @@ struct View {
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
     double* zprob;  // [n][Cp] or NULL
+    double* eps;    // [n_pad][Cp]  probit only
+    double* G0;     // [M_pad]      probit only: vech of [X K]'[X K], shared by all chains
     int32_t* status;  // [Cp]
     Control* ctl;
 };
@@ -126,7 +128,7 @@ struct Carver {
 static int fill_dims(const occu_problem_t* P, View& v) {
     if (!P) return set_err("null problem");
     if (P->abi_version != OCCU_ABI_VERSION) return set_err("ABI version mismatch");
-    if (P->model != OCCU_LOGIT_RSR) return set_err("model not implemented in this build");
+    if (P->model != OCCU_LOGIT_RSR && P->model != OCCU_PROBIT_RSR) return set_err("model not implemented in this build");
     if (P->n < 1 || P->p < 1 || P->r < 1 || P->chains < 1 || P->V < 0) return set_err("bad dimensions");
     if (P->p > MAX_SMALL || P->r > 8) return set_err("p must be <= 32 and r <= 8");
     if (P->q < 1) return set_err("RSR model needs q >= 1");
@@ -144,6 +146,13 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     v.ldh = round_up(v.pq, dgemm::BN);
     v.ldz = v.M_pad + v.ldh;
     v.ksplit = (v.n_pad / dgemm::BK >= 64) ? 8 : 1;
+    if (P->model == OCCU_PROBIT_RSR) {
+        // only the K-split product U'd runs: split it until the grid covers the GPU (2 CTAs x 148 SMs)
+        const int tiles = (v.Cp / dgemm::BM) * (v.ldh / dgemm::BN);
+        int ks = (296 + tiles - 1) / tiles;
+        const int kt = v.n_pad / dgemm::BK;
+        v.ksplit = ks < 1 ? 1 : (ks > kt ? kt : (ks > 64 ? 64 : ks));
+    }
     v.n_tiles = (P->n + SITE_TILE - 1) / SITE_TILE;
     v.NV = P->r * (P->r + 1) / 2 + P->r;
     // solve kernel keeps the packed joint Gram + H + a few vectors in shared memory
@@ -171,7 +180,10 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.omega = c.take<double>((size_t)v.n_pad * Cp);
     v.kd = c.take<double>((size_t)v.n_pad * Cp);
     v.z = c.take<uint8_t>((size_t)v.n * Cp);
-    v.G = c.take<double>(Cp * (size_t)v.M_pad);
+    const bool probit = v.model == OCCU_PROBIT_RSR;
+    v.G = probit ? nullptr : c.take<double>(Cp * (size_t)v.M_pad);
+    v.eps = probit ? c.take<double>((size_t)v.n_pad * Cp) : nullptr;
+    v.G0 = probit ? c.take<double>(v.M_pad) : nullptr;
     v.Hpart = c.take<double>((size_t)v.ksplit * Cp * v.ldh);
     v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
     v.asum = c.take<double>((size_t)v.NV * Cp);
@@ -405,6 +417,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
 // Variant used by occu_debug_gaussian_half when omega_a is injected: alpha partial sums only.
 template <int R>
 __global__ void __launch_bounds__(CHAIN_TILE) alpha_partials_injected_kernel(const View v, const double* __restrict__ omega_a_cm) {
+    const bool probit = v.model == OCCU_PROBIT_RSR;
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
     const int tile = blockIdx.x;
@@ -422,8 +435,8 @@ __global__ void __launch_bounds__(CHAIN_TILE) alpha_partials_injected_kernel(con
             double w[R];
 #pragma unroll
             for (int k = 0; k < R; k++) w[k] = v.W[(size_t)vv * R + k];
-            const double om = oma[vv];
-            const double yk = (double)v.y[vv] - 0.5;
+            const double om = probit ? 1.0 : oma[vv];                               // probit.py:233 vs logit.py:222
+            const double yk = probit ? oma[vv] : (double)v.y[vv] - 0.5;             // probit.py:234 vs logit.py:223
             int idx = 0;
 #pragma unroll
             for (int a = 0; a < R; a++) {
@@ -433,6 +446,124 @@ __global__ void __launch_bounds__(CHAIN_TILE) alpha_partials_injected_kernel(con
 #pragma unroll
             for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;
         }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
+}
+
+// G0[m] = sum_i Z[i][m]: the joint Gram of [X K] with unit weights (probit: K'K, K'X, X'X; probit.py:112, 144)
+__global__ void gram_unit_kernel(View v) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= v.M) return;
+    double s = 0.0;
+    for (int i = 0; i < v.n; i++) s += v.ZU[(size_t)i * v.ldz + m];
+    v.G0[m] = s;
+}
+
+// injected randomness for the parity tests (all chain-major, NULL = Philox)
+struct SiteDebug {
+    const double* u_site;   // [C][n]  uniforms of the omega_b truncated normals (probit.py:203-209)
+    const double* u_visit;  // [C][V]  uniforms of the omega_a truncated normals (probit.py:191-194)
+    const double* nrm_eps;  // [C][n]  normals of the eps update (probit.py:220)
+    int keep_z;             // 1: do not redraw z (the reference draws omega_b from the CURRENT z)
+};
+
+// ------------------------------------------------------------------------------------------------
+// site pass (probit): z | ., omega_a (truncated normal) + alpha partial sums, omega_b, eps, d = omega_b - eps
+// No rejection loops (inverse-CDF draws), so the lanes stay in lock-step over the sites of the tile.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
+    constexpr int NA = R * (R + 1) / 2, NV = NA + R;
+    const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
+    const int tile = blockIdx.x;
+    const int i0 = tile * SITE_TILE;
+    const int i1 = min(i0 + SITE_TILE, v.n);
+    const uint32_t iter = v.ctl->iter;
+    const bool keep_z = v.ctl->first != 0 || dbg.keep_z;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const size_t Cp = v.Cp;
+    const int cr = c % v.C;
+
+    double al[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) al[k] = v.alpha[(size_t)k * Cp + c];
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.0;
+
+    for (int i = i0; i < i1; i++) {
+        const int cls = v.site_class[i];
+        const size_t off = (size_t)i * Cp + c;
+        const double lp = v.psi[off];   // x_i beta + K_i eta
+        const double ep = v.eps[off];
+        const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
+        int zc;
+        if (keep_z) {
+            zc = v.z[off];
+        } else {
+            if (cls == OCCU_SITE_OBS) {
+                zc = 1;
+            } else {
+                double pr = ndtr_d(lp + ep);  // probit.py:251 / 258
+                if (cls == OCCU_SITE_NOT_OBS) {
+                    double prod = 1.0;  // probit.py:252-253: prod_j (1 - Phi(w_ij alpha))
+                    for (int vv = v0; vv < v1; vv++) {
+                        double lin = 0.0;
+#pragma unroll
+                        for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                        prod *= 1.0 - ndtr_d(lin);
+                    }
+                    const double num = pr * prod;
+                    pr = num / ((1.0 - pr) + num);  // probit.py:254-255
+                }
+                if (v.zprob) v.zprob[off] = pr;
+                Philox g;
+                g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
+                zc = g.unif_d() < pr ? 1 : 0;
+            }
+            v.z[off] = (uint8_t)zc;
+        }
+        if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
+            // omega_a ~ TN(w_ij alpha, 1) on (0, inf) if y_ij = 1 else (-inf, 0)   (probit.py:180-194)
+            for (int vv = v0; vv < v1; vv++) {
+                double w[R];
+                double lin = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    w[k] = v.W[(size_t)vv * R + k];
+                    lin += w[k] * al[k];
+                }
+                const bool positive = v.y[vv] == 1;
+                double oma;
+                if (dbg.u_visit) {
+                    oma = truncnorm_icdf(lin, positive, dbg.u_visit[(size_t)cr * v.V + vv]);
+                } else {
+                    Philox g;
+                    g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
+                    oma = truncnorm_draw(lin, positive, g);
+                }
+                int idx = 0;
+#pragma unroll
+                for (int a = 0; a < R; a++) {
+#pragma unroll
+                    for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
+                }
+#pragma unroll
+                for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
+            }
+        }
+        // omega_b ~ TN(lp + eps, 1), sign by z (probit.py:196-209); eps | . (probit.py:216-221)
+        Philox g;
+        g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
+        const double loc = lp + ep;
+        const double omb = dbg.u_site ? truncnorm_icdf(loc, zc == 1, dbg.u_site[(size_t)cr * v.n + i])
+                                      : truncnorm_draw(loc, zc == 1, g);
+        const double nz = dbg.nrm_eps ? dbg.nrm_eps[(size_t)cr * v.n + i] : g.normal_d();
+        const double ep_new = 0.5 * (omb - lp) + nz * 0.70710678118654752440;
+        v.omega[off] = omb;
+        v.eps[off] = ep_new;
+        v.kd[off] = omb - ep_new;  // d: right-hand-side vector of both the eta and the beta systems
     }
 #pragma unroll
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
@@ -541,7 +672,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     const uint32_t gc = (uint32_t)(v.chain_offset + c);
     const int cr = c % v.C;  // chain whose injected values a padded chain replicates
 
-    const double* Grow = v.G + (size_t)c * v.M_pad;
+    // logit: per-chain omega-weighted Gram; probit: the shared unit-weight Gram (A_eta = K'K + tau Q, probit.py:226)
+    const double* Grow = v.model == OCCU_PROBIT_RSR ? v.G0 : v.G + (size_t)c * v.M_pad;
     for (int m = tid; m < M; m += T) Gs[m] = Grow[m];
     for (int a = tid; a < pq; a += T) {
         double hs = 0.0;  // K-split partials, fixed order
@@ -892,7 +1024,7 @@ __global__ void chain_summaries_kernel(const double* __restrict__ rec, int chain
 // host-side drivers
 // ------------------------------------------------------------------------------------------------
 template <typename PGT>
-static void launch_site_pass(occu_engine* e, cudaStream_t st) {
+static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
     switch (v.r) {
@@ -901,6 +1033,23 @@ static void launch_site_pass(occu_engine* e, cudaStream_t st) {
 #undef CASE
     }
     e->launches++;
+}
+
+static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t st) {
+    const View& v = e->v;
+    if (v.model == OCCU_PROBIT_RSR) {
+        dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
+        switch (v.r) {
+#define CASE(R) case R: site_pass_probit_kernel<R><<<grid, CHAIN_TILE, 0, st>>>(v, dbg); break;
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+        }
+        e->launches++;
+    } else if (e->pg_fp64) {
+        launch_site_pass_logit<double>(e, st);
+    } else {
+        launch_site_pass_logit<float>(e, st);
+    }
 }
 
 static void launch_alpha_injected(occu_engine* e, const double* omega_a, cudaStream_t st) {
@@ -931,7 +1080,7 @@ static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     dgemm::Args a;
     memset(&a, 0, sizeof(a));
     a.A1 = v.omega; a.B = v.ZU; a.Out = v.G;
-    a.M = v.Cp; a.N = v.M_pad; a.K = v.n_pad;
+    a.M = v.Cp; a.N = v.model == OCCU_PROBIT_RSR ? 0 : v.M_pad; a.K = v.n_pad;  // probit: only U'd
     a.lda = v.Cp; a.ldb = v.ldz; a.ldo = v.M_pad;
     a.A2 = v.kd; a.Out2 = v.Hpart; a.N2 = v.ldh; a.col2 = v.M_pad; a.ldo2 = v.ldh; a.ksplit = v.ksplit;
     CUDA_OK(dgemm::launch(a, st));
@@ -1065,6 +1214,10 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     FAIL_IF(cudaMemcpyAsync((void*)v.Qrsr, P->Qrsr, (size_t)v.q * v.q * 8, cudaMemcpyDeviceToDevice, st));
     build_design_kernel<<<v.n, 128, v.pq * sizeof(double), st>>>(v, P->X, P->K);
     e->launches++;
+    if (v.model == OCCU_PROBIT_RSR) {
+        gram_unit_kernel<<<(v.M + 127) / 128, 128, 0, st>>>(v);
+        e->launches++;
+    }
     const size_t total = (size_t)v.n * v.Cp;
     reset_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
     set_control_kernel<<<1, 1, 0, st>>>(v.ctl, 0u, 1, -1, 1);
@@ -1110,6 +1263,9 @@ static int field_info(const occu_engine* e, int field, void** ptr, int* d, int* 
         case OCCU_F_Z: *ptr = v.z; *d = v.n; *is_u8 = 1; return 0;
         case OCCU_F_OMEGA: *ptr = v.omega; *d = v.n; return 0;
         case OCCU_F_PSI: *ptr = v.psi; *d = v.n; return 0;
+        case OCCU_F_EPS:
+            if (!v.eps) return set_err("EPS exists for the probit model only");
+            *ptr = v.eps; *d = v.n; return 0;
         case OCCU_F_ZPROB:
             if (!v.zprob) return set_err("ZPROB needs a debug engine");
             *ptr = v.zprob; *d = v.n; return 0;
@@ -1195,12 +1351,13 @@ int occu_sweep(occu_engine_t* e, int n_iters, double* rec_alpha, double* rec_bet
     }
     SolveDebug dbg;
     memset(&dbg, 0, sizeof(dbg));
+    SiteDebug sdbg;
+    memset(&sdbg, 0, sizeof(sdbg));
     for (int it = 0; it < n_iters; it++) {
         PROF_MARK(e, KC_PSI_GEMM, st);
         if (launch_psi_gemm(e, st)) return -1;
         PROF_MARK(e, KC_SITE_PASS, st);
-        if (e->pg_fp64) launch_site_pass<double>(e, st);
-        else launch_site_pass<float>(e, st);
+        launch_site_pass(e, sdbg, st);
         if (launch_gaussian_half(e, dbg, rec_alpha, rec_beta, rec_tau, rec_capacity, st)) return -1;
         advance_kernel<<<1, 1, 0, st>>>(v.ctl);
         e->launches++;
@@ -1226,19 +1383,24 @@ int occu_debug_gaussian_half(occu_engine_t* e, const double* normals, const doub
     return read_fails(e, st);
 }
 
-int occu_debug_site_half(occu_engine_t* e, void* stream) {
+int occu_debug_site_half(occu_engine_t* e, int keep_z, const double* u_site, const double* u_visit,
+                         const double* nrm_eps, void* stream) {
     if (!e) return set_err("null engine");
     if (!e->debug) return set_err("engine was not created with debug = 1");
     cudaStream_t st = (cudaStream_t)stream;
+    SiteDebug sdbg;
+    sdbg.u_site = u_site;
+    sdbg.u_visit = u_visit;
+    sdbg.nrm_eps = nrm_eps;
+    sdbg.keep_z = keep_z;
     // force the z-update branch even on a fresh engine
     Control h;
     CUDA_OK(cudaMemcpyAsync(&h, e->v.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    set_control_kernel<<<1, 1, 0, st>>>(e->v.ctl, h.iter, 0, -1, 0);
+    set_control_kernel<<<1, 1, 0, st>>>(e->v.ctl, h.iter, keep_z ? 1 : 0, -1, 0);
     e->launches++;
     if (launch_psi_gemm(e, st)) return -1;
-    if (e->pg_fp64) launch_site_pass<double>(e, st);
-    else launch_site_pass<float>(e, st);
+    launch_site_pass(e, sdbg, st);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(st));
     return 0;

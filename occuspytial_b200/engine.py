@@ -101,8 +101,8 @@ class DeviceEngine:
     def set_field(self, field, values):
         torch = self.torch
         dtype = np.uint8 if field == _lib.F_Z else np.float64
-        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=dtype),
-                                                   (self.chains,) + self._field_shape(field)))
+        arr = np.array(np.broadcast_to(np.asarray(values, dtype=dtype), (self.chains,) + self._field_shape(field)),
+                       order='C', copy=True)
         self.h2d_bytes += arr.nbytes
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             t = torch.from_numpy(arr).to(self.device)
@@ -177,7 +177,7 @@ class DeviceEngine:
             def dev(a, shape):
                 if a is None:
                     return None
-                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), shape))
+                a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), shape), order='C', copy=True)
                 return torch.from_numpy(a).to(self.device)
             tn, tt, to = dev(normals, (C_, q + p + r)), dev(tau, (C_,)), dev(omega_a, (C_, self.V))
             shapes = dict(eta_prec=(C_, q, q), eta_b=(C_, q), eta_chol=(C_, q, q), eta_mean=(C_, q),
@@ -192,9 +192,19 @@ class DeviceEngine:
         res['fails'] = fails
         return res
 
-    def debug_site_half(self):
-        with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.occu_debug_site_half(self.handle, self.stream.cuda_stream), 'occu_debug_site_half')
+    def debug_site_half(self, keep_z=False, u_site=None, u_visit=None, nrm_eps=None):
+        torch = self.torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            def dev(a, shape):
+                if a is None:
+                    return None
+                a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), shape), order='C', copy=True)
+                return torch.from_numpy(a).to(self.device)
+            ts, tv, te = dev(u_site, (self.chains, self.n)), dev(u_visit, (self.chains, self.V)), dev(nrm_eps, (self.chains, self.n))
+            ptr = lambda t: None if t is None else t.data_ptr()
+            _lib.check(self.lib.occu_debug_site_half(self.handle, int(bool(keep_z)), ptr(ts), ptr(tv), ptr(te),
+                                                     self.stream.cuda_stream), 'occu_debug_site_half')
+            self.stream.synchronize()
 
     def close(self):
         if getattr(self, 'handle', None) is not None:

@@ -1,0 +1,129 @@
+"""GPU parity tests of the ProbitRSRGibbs sweep: reference golden vectors (first, uncorrupted call of every
+update, probit.py:173-260) and the oracle's corrected sampler."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _sampler_from_golden(g, cls, **kw):
+    ptr = g['visit_ptr']
+    W = {int(s): g['W_rows'][ptr[s]:ptr[s + 1]] for s in g['surveyed_order']}
+    y = {int(s): g['y_rows'][ptr[s]:ptr[s + 1]] for s in g['surveyed_order']}
+    return cls(sparse.csc_matrix(g['Q']), W, g['X'], y, **kw)
+
+
+def test_probit_iteration_vs_reference_golden():
+    from occuspytial_b200 import ProbitRSRGibbs, _lib
+    g = golden('probit_rsr.npz')
+    s = _sampler_from_golden(g, ProbitRSRGibbs, K=g['K'], random_state=1)
+    np.testing.assert_allclose(s.fixed.KTK, g['KTK'], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(s.fixed.XTX_plus_bprec, g['XTX_plus_bprec'], rtol=1e-13)
+    eng = s._make_engine(3, seed=5, debug=True)
+    eng.set_start(dict(alpha=g['st_alpha'], beta=g['st_beta'], tau=g['st_tau'], eta=g['st_eta'], eps=g['st_eps']))
+    eng.set_field(_lib.F_Z, g['st_z'].astype(np.uint8))
+    # omega_b, eps, omega_a with the reference's uniforms / normals and the CURRENT z (probit.py:262-264)
+    eng.debug_site_half(keep_z=True, u_site=g['u_omega_b'], u_visit=g['u_omega_a_rows'], nrm_eps=g['eps_normals'])
+    np.testing.assert_allclose(eng.get_field(_lib.F_OMEGA)[1], g['omega_b'], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(eng.get_field(_lib.F_EPS)[2], g['eps_out'], rtol=1e-10, atol=1e-12)
+    q = g['K'].shape[1]
+    normals = np.concatenate([g['eta_normals'], g['beta_normals'], g['alpha_normals']])
+    out = eng.debug_gaussian_half(normals=normals, tau=g['st_tau'])
+    assert out['fails'] == 0
+    np.testing.assert_allclose(out['tau_rate'], g['tau_rate_out'], rtol=1e-11)
+    np.testing.assert_allclose(out['eta_prec'][0], g['KTK'] + g['st_tau'] * g['Qrsr'], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(eng.get_field(_lib.F_ETA)[0], g['eta_out'], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out['beta_prec'][1], g['XTX_plus_bprec'], rtol=1e-11)
+    np.testing.assert_allclose(eng.get_field(_lib.F_BETA)[1], g['beta_out'], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(eng.get_field(_lib.F_ALPHA)[2], g['alpha_out'], rtol=1e-9, atol=1e-11)
+    # z probabilities from the updated (alpha, beta, eta, eps)   (probit.py:245-260)
+    eng.debug_site_half()
+    zp = eng.get_field(_lib.F_ZPROB)[0]
+    np.testing.assert_allclose(zp[g['not_obs']], g['p_no'], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(zp[g['not_surveyed']], g['p_ns'], rtol=1e-10, atol=1e-14)
+    assert np.all(eng.get_field(_lib.F_Z)[:, g['obs']] == 1)
+    eng.close()
+
+
+def test_probit_pieces_vs_oracle_multichain():
+    from occuspytial_b200 import ProbitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from oracle import sweep as S
+    Q, W, X, y, *_ = make_data(n=300, min_v=1, max_v=6, ns=170, p=4, q=3, random_state=3)
+    chains, q, p, r = 130, 21, 4, 3
+    s = ProbitRSRGibbs(Q, W, X, y, random_state=2, q=q)
+    f = s.fixed
+    prob = s._problem_arrays()
+    V, n = prob['W_rows'].shape[0], f.n
+    rng = np.random.default_rng(8)
+    eng = s._make_engine(chains, seed=11, debug=True)
+    st = dict(alpha=rng.normal(size=(chains, r)), beta=rng.normal(size=(chains, p)), tau=rng.uniform(0.3, 3, chains),
+              eta=rng.normal(size=(chains, q)), eps=rng.normal(size=(chains, n)))
+    eng.set_start(st)
+    eng.debug_site_half()          # fresh z from the start state
+    z = eng.get_field(_lib.F_Z).astype(float)
+    eng.set_field(_lib.F_EPS, st['eps'])   # the site half also advanced eps; restore the start value
+    u_site, u_visit, nz = rng.random((chains, n)), rng.random((chains, V)), rng.normal(size=(chains, n))
+    eng.debug_site_half(keep_z=True, u_site=u_site, u_visit=u_visit, nrm_eps=nz)
+    omega, eps_new = eng.get_field(_lib.F_OMEGA), eng.get_field(_lib.F_EPS)
+    normals = rng.normal(size=(chains, q + p + r))
+    out = eng.debug_gaussian_half(normals=normals, tau=st['tau'])
+    eta_new, beta_new, alpha_new = eng.get_field(_lib.F_ETA), eng.get_field(_lib.F_BETA), eng.get_field(_lib.F_ALPHA)
+    vptr, Wd, yd = prob['visit_ptr'], prob['W_rows'], prob['y_rows'].astype(float)
+    KTK, XTXb = f.K.T @ f.K, X.T @ X + f.b_prec
+    for c in (0, 1, 63, 64, 127, 128, 129):
+        spatial = f.K @ st['eta'][c]
+        ob = S.probit_omega_b(X, st['beta'][c], spatial, st['eps'][c], z[c], u_site[c])
+        np.testing.assert_allclose(omega[c], ob, rtol=1e-10, atol=1e-12)
+        ep = S.probit_eps(ob, X, st['beta'][c], spatial, nz[c])
+        np.testing.assert_allclose(eps_new[c], ep, rtol=1e-10, atol=1e-12)
+        A, b = S.probit_eta_system(f.K, KTK, f.Q, X, ob, st['beta'][c], ep, st['tau'][c])
+        np.testing.assert_allclose(out['eta_prec'][c], A, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out['eta_b'][c], b, rtol=1e-9, atol=1e-10)
+        eta_o = S.precision_mvnorm(b, A, normals[c, :q])[0]
+        np.testing.assert_allclose(eta_new[c], eta_o, rtol=1e-9, atol=1e-10)
+        A, b = S.probit_beta_system(X, XTXb, ob, f.K @ eta_new[c], ep, f.b_prec_by_mu)
+        np.testing.assert_allclose(out['beta_b'][c], b, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(beta_new[c], S.precision_mvnorm(b, A, normals[c, q:q + p])[0], rtol=1e-9, atol=1e-10)
+        rows = np.concatenate([np.arange(vptr[i], vptr[i + 1]) for i in range(n) if f.site_class[i] != 0 and z[c][i] == 1])
+        oa = S.probit_omega_a(Wd[rows], yd[rows], st['alpha'][c], u_visit[c][rows])
+        A, b = S.probit_alpha_system(Wd[rows], oa, f.a_prec, f.a_prec_by_mu)
+        np.testing.assert_allclose(out['alpha_prec'][c], A, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out['alpha_b'][c], b, rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(alpha_new[c], S.precision_mvnorm(b, A, normals[c, q + p:])[0], rtol=1e-9, atol=1e-10)
+    eng.close()
+
+
+def test_probit_sampler_api_and_posterior_vs_oracle():
+    """The reference's own ProbitRSRGibbs tests are xfail (it diverges); here they must pass, and the posterior
+    must agree with the oracle's corrected CPU sampler within 3 MCSE."""
+    from occuspytial_b200 import ProbitRSRGibbs
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.diagnostics import summaries_from_draws, ess
+    from oracle import sweep as S
+    Q, W, X, y, *_ = make_data(min_v=2, max_v=10, ns=100, p=3, q=2, random_state=10)
+    s = ProbitRSRGibbs(Q, W, X, y, random_state=10)
+    a = s.sample(5, chains=1, progressbar=False)
+    assert a['alpha'].shape == (1, 5, 2) and a['beta'].shape == (1, 5, 3) and a['tau'].shape == (1, 5)
+    b = ProbitRSRGibbs(Q, W, X, y, random_state=10).sample(5, chains=1, progressbar=False)
+    assert np.allclose(a['alpha'], b['alpha']) and np.allclose(a['tau'], b['tau'])
+    with pytest.raises(ValueError, match='Threshold value needs to be in'):
+        ProbitRSRGibbs(Q, W, X, y, r=1.1)
+    hp = {'tau_rate': 1.0, 'tau_shape': 5.0, 'a_mu': np.zeros(2), 'b_mu': np.zeros(3), 'a_prec': np.eye(2) / 10,
+          'b_prec': np.eye(3) / 10}
+    s = ProbitRSRGibbs(Q, W, X, y, hparams=hp, random_state=3, q=10)
+    post = s.sample(1500, burnin=500, chains=256, progressbar=False)
+    assert np.all(np.isfinite(post['beta']))
+    ref = S.run_chains('probit_rsr', Q, W, X, y, 3000, 1000, chains=4, seed=5, hparams=hp, K=s.fixed.K)
+
+    def mean_mcse(x):
+        x = x.reshape(x.shape[0], x.shape[1], -1)
+        return [(x[:, :, k].mean(), x[:, :, k].std(ddof=1) / np.sqrt(ess(summaries_from_draws(x[:, :, k], 200), x.shape[1])))
+                for k in range(x.shape[2])]
+
+    for name in ('alpha', 'beta', 'tau'):
+        for (mr, sr), (mm, sm) in zip(mean_mcse(ref[name]), mean_mcse(post[name])):
+            assert abs(mr - mm) < 3.0 * np.hypot(sr, sm), (name, mr, mm, sr, sm)
