@@ -66,7 +66,7 @@ struct HParams {
 // device view of an engine (passed to kernels by value)
 struct View {
     int model, n, p, r, q, pq, V, C, Cp, chain_offset;
-    int n_pad, kq_pad, M, M_pad, ldz, ldh, ksplit, n_tiles, NV;
+    int n_pad, kq_pad, M, M_pad, ldz, ldh, ksplit, n_tiles, NV, bw;
     uint64_t seed;
     const double* W;
     const uint8_t* y;
@@ -89,6 +89,12 @@ struct View {
     double* asum;   // [NV][Cp]
     double* zprob;  // [n][Cp] or NULL
     double* eps;    // [n_pad][Cp]  probit only
+    // ICAR only
+    const double* X;      // [n][p]
+    const double* Qband;  // [n][bw + 1]   Qband[i][d] = Q[i][i - d]
+    double* eta_n;        // [n_pad][Cp]   eta (= spatial effect), chain-minor
+    double* Lc;           // [Cp][n][bw + 1]  column-band Cholesky factor, Lc[j][e] = L[j + e][j]
+    double* scratch;      // [Cp][6][n]    y_b, y_1, x, zv, mean, spare
     double* G0;     // [M_pad]      probit only: vech of [X K]'[X K], shared by all chains
     int32_t* status;  // [Cp]
     Control* ctl;
@@ -128,13 +134,19 @@ struct Carver {
 static int fill_dims(const occu_problem_t* P, View& v) {
     if (!P) return set_err("null problem");
     if (P->abi_version != OCCU_ABI_VERSION) return set_err("ABI version mismatch");
-    if (P->model != OCCU_LOGIT_RSR && P->model != OCCU_PROBIT_RSR) return set_err("model not implemented in this build");
+    if (P->model != OCCU_LOGIT_RSR && P->model != OCCU_PROBIT_RSR && P->model != OCCU_LOGIT_ICAR)
+        return set_err("unknown model id");
+    const bool icar = P->model == OCCU_LOGIT_ICAR;
     if (P->n < 1 || P->p < 1 || P->r < 1 || P->chains < 1 || P->V < 0) return set_err("bad dimensions");
     if (P->p > MAX_SMALL || P->r > 8) return set_err("p must be <= 32 and r <= 8");
-    if (P->q < 1) return set_err("RSR model needs q >= 1");
+    if (!icar && P->q < 1) return set_err("RSR model needs q >= 1");
+    if (icar && (P->icar_bw < 1 || P->icar_bw >= P->n)) return set_err("ICAR model needs 1 <= icar_bw < n");
+    if (icar && ((size_t)(P->icar_bw + 1) * (P->icar_bw + 2) + 8 * (size_t)(P->icar_bw + 1) + 4096) * 8 > 200 * 1024)
+        return set_err("ICAR half bandwidth too large for the shared-memory window (reorder the sites)");
+    v.bw = icar ? P->icar_bw : 0;
     v.model = P->model;
-    v.n = P->n; v.p = P->p; v.r = P->r; v.q = P->q; v.V = P->V;
-    v.pq = P->p + P->q;
+    v.n = P->n; v.p = P->p; v.r = P->r; v.q = icar ? 0 : P->q; v.V = P->V;
+    v.pq = v.p + v.q;
     v.C = P->chains;
     v.Cp = round_up(P->chains, CHAIN_TILE);
     v.chain_offset = P->chain_offset;
@@ -170,9 +182,15 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.y = c.take<uint8_t>((size_t)v.V + 1);
     v.visit_ptr = c.take<int32_t>((size_t)v.n + 1);
     v.site_class = c.take<uint8_t>(v.n);
-    v.Qrsr = c.take<double>((size_t)v.q * v.q);
-    v.UT = c.take<double>((size_t)v.kq_pad * v.n_pad);
-    v.ZU = c.take<double>((size_t)v.n_pad * v.ldz);
+    const bool icar = v.model == OCCU_LOGIT_ICAR;
+    v.Qrsr = icar ? nullptr : c.take<double>((size_t)v.q * v.q);
+    v.UT = icar ? nullptr : c.take<double>((size_t)v.kq_pad * v.n_pad);
+    v.ZU = icar ? nullptr : c.take<double>((size_t)v.n_pad * v.ldz);
+    v.X = icar ? c.take<double>((size_t)v.n * v.p) : nullptr;
+    v.Qband = icar ? c.take<double>((size_t)v.n * (v.bw + 1)) : nullptr;
+    v.eta_n = icar ? c.take<double>((size_t)v.n_pad * Cp) : nullptr;
+    v.Lc = icar ? c.take<double>(Cp * (size_t)v.n * (v.bw + 1)) : nullptr;
+    v.scratch = icar ? c.take<double>(Cp * (size_t)6 * v.n) : nullptr;
     v.theta = c.take<double>((size_t)v.kq_pad * Cp);
     v.alpha = c.take<double>((size_t)v.r * Cp);
     v.tau = c.take<double>(Cp);
@@ -181,10 +199,10 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.kd = c.take<double>((size_t)v.n_pad * Cp);
     v.z = c.take<uint8_t>((size_t)v.n * Cp);
     const bool probit = v.model == OCCU_PROBIT_RSR;
-    v.G = probit ? nullptr : c.take<double>(Cp * (size_t)v.M_pad);
+    v.G = (probit || icar) ? nullptr : c.take<double>(Cp * (size_t)v.M_pad);
     v.eps = probit ? c.take<double>((size_t)v.n_pad * Cp) : nullptr;
     v.G0 = probit ? c.take<double>(v.M_pad) : nullptr;
-    v.Hpart = c.take<double>((size_t)v.ksplit * Cp * v.ldh);
+    v.Hpart = icar ? nullptr : c.take<double>((size_t)v.ksplit * Cp * v.ldh);
     v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
     v.asum = c.take<double>((size_t)v.NV * Cp);
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
@@ -1021,6 +1039,343 @@ __global__ void chain_summaries_kernel(const double* __restrict__ rec, int chain
 }
 
 // ------------------------------------------------------------------------------------------------
+// LogitICARGibbs ("PGGibbs"): eta | . ~ N(Lambda^-1 b, Lambda^-1) on {1'eta = 0}, Lambda = tau Q + diag(omega_b)
+//
+// The reference perturbs b through a dense eigen-factor of Q (2n - 1 normals) and solves two systems with
+// MINRES at rtol 1e-5 (logit.py:73-99).  Here Lambda -- whose sparsity pattern is fixed by Q -- is factorised
+// exactly per chain by a banded Cholesky over the fixed symbolic pattern (half bandwidth bw after the host's
+// reordering), the draw is x = Lambda^-1 b + L^-T eps (n normals, same law), zv = Lambda^-1 1, and
+// eta = x - (sum x / sum zv) zv (ensure_sums_to_zero, distributions.pyx:24-39).
+//
+// One CTA per chain.  Right-looking column Cholesky on a (bw+1) x (bw+1) ring-indexed window in shared
+// memory (no data movement when the window slides), forward substitution of both right-hand sides fused
+// into the factorisation, L streamed to HBM once in column-band form and read back once by the backward pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int ICAR_THREADS = 128;
+
+// psi = X beta + eta   (logit.py:201 with spatial = eta)
+__global__ void psi_icar_kernel(const View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)v.n * v.Cp;
+    if (idx >= total) return;
+    const int i = (int)(idx / v.Cp), c = (int)(idx - (size_t)i * v.Cp);
+    double s = v.eta_n[idx];
+    for (int a = 0; a < v.p; a++) s += v.X[(size_t)i * v.p + a] * v.theta[(size_t)a * v.Cp + c];
+    v.psi[idx] = s;
+}
+
+__device__ __forceinline__ double block_sum_128(double val, double* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(ICAR_THREADS) solve_logit_icar_kernel(const View v, const SolveDebug dbg,
+                                                                         double* rec_alpha, double* rec_beta,
+                                                                         double* rec_tau, int rec_capacity) {
+    extern __shared__ double sm[];
+    const int c = blockIdx.x, tid = threadIdx.x, T = ICAR_THREADS;
+    const int n = v.n, p = v.p, r = v.r, w = v.bw, W1 = v.bw + 1;
+    const size_t Cp = v.Cp;
+    const HParams* hp = v.hp;
+    double* Wn = sm;                     // [W1][W1] ring window, element (i, k) at Wn[(i % W1) * W1 + (k % W1)]
+    double* col = Wn + W1 * W1;          // [W1] current column of L
+    double* r1 = col + W1;               // [W1] ring: forward residual of b
+    double* r2 = r1 + W1;                // [W1] ring: forward residual of 1
+    double* xr = r2 + W1;                // [3][W1] rings of the backward solves
+    double* nrm = xr + 3 * W1;           // [p + r] normals of beta, alpha
+    double* red = nrm + 2 * MAX_SMALL;   // [8]
+    uint8_t* pair_i = reinterpret_cast<uint8_t*>(red + 8);  // [w (w+1) / 2] trailing-update pair table
+    uint8_t* pair_k = pair_i + (w * (w + 1)) / 2;
+    __shared__ double small_S[MAX_SMALL * MAX_SMALL];
+    __shared__ double small_b[MAX_SMALL], small_x[MAX_SMALL], small_t[MAX_SMALL], beta_s[MAX_SMALL];
+    __shared__ double ybc[2];
+    __shared__ int ok_flag;
+
+    const uint32_t iter = v.ctl->iter;
+    const int rec_index = v.ctl->rec_index;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const int cr = c % v.C;
+    double* Lc = v.Lc + (size_t)c * n * W1;
+    double* yb = v.scratch + (size_t)c * 6 * n;  // forward results / backward inputs
+    double* y1 = yb + n;
+    double* xs = y1 + n;
+    double* zs = xs + n;
+    double* ms = zs + n;
+
+    for (int a = tid; a < p; a += T) beta_s[a] = v.theta[(size_t)a * Cp + c];
+    for (int k = tid; k < p + r; k += T) {
+        double val;
+        if (dbg.normals) {
+            val = dbg.normals[(size_t)cr * (n + p + r) + n + k];
+        } else {
+            Philox g;
+            g.init(v.seed, gc, (uint32_t)(n + k), iter, ST_NORMALS);
+            val = g.normal_d();
+        }
+        nrm[k] = val;
+    }
+    {
+        int t = 0;  // pair table (ii, kk), kk <= ii < w, built redundantly but cheaply by thread 0..: parallel fill
+        for (int ii = 0; ii < w; ii++) {
+            for (int kk = tid; kk <= ii; kk += T) {
+                pair_i[t + kk] = (uint8_t)ii;
+                pair_k[t + kk] = (uint8_t)kk;
+            }
+            t += ii + 1;
+        }
+    }
+    if (tid == 0) ok_flag = 1;
+    __syncthreads();
+
+    // ---- tau | eta: rate = eta' Q eta / 2 + tau_rate (logit.py:206-209), Q in lower-band form ----
+    double part = 0.0;
+    for (int i = tid; i < n; i += T) {
+        const double ei = v.eta_n[(size_t)i * Cp + c];
+        double s = 0.5 * v.Qband[(size_t)i * W1] * ei;
+        const int dmax = min(w, i);
+        for (int d = 1; d <= dmax; d++) s += v.Qband[(size_t)i * W1 + d] * v.eta_n[(size_t)(i - d) * Cp + c];
+        part += ei * s;  // eta' Q eta = 2 * sum_i eta_i (Q_ii eta_i / 2 + sum_{k<i} Q_ik eta_k)
+    }
+    const double quad = 2.0 * block_sum_128(part, red, tid);
+    __syncthreads();
+    if (tid == 0) {
+        const double rate = 0.5 * quad + hp->tau_rate;
+        double tau;
+        if (dbg.tau_in) {
+            tau = dbg.tau_in[cr];
+        } else {
+            Philox g;
+            g.init(v.seed, gc, 0u, iter, ST_TAU);
+            tau = gamma_draw(hp->tau_shape, g) / rate;
+        }
+        red[4] = tau;
+        if (dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
+    }
+    __syncthreads();
+    const double tau = red[4];
+
+    // row i of Lambda (band part) and of the right-hand sides enters ring slot i % W1
+    auto load_row = [&](int i) {
+        const int slot = i % W1;
+        for (int d = tid; d < W1; d += T) {  // k = i - d
+            double val = 0.0;
+            if (i < n) {
+                if (d <= i) val = tau * v.Qband[(size_t)i * W1 + d];
+                if (d == 0) val += v.omega[(size_t)i * Cp + c];
+            } else if (d == 0) {
+                val = 1.0;  // identity padding past the last row
+            }
+            const int k = i - d;
+            const int kslot = ((k % W1) + W1) % W1;
+            Wn[slot * W1 + kslot] = val;
+        }
+        if (tid == 0) {
+            // b_i = k_i - omega_i x_i'beta   (logit.py:213)
+            double bi = 0.0, one = 0.0;
+            if (i < n) {
+                double xb = 0.0;
+                for (int a = 0; a < p; a++) xb += v.X[(size_t)i * p + a] * beta_s[a];
+                bi = v.kd[(size_t)i * Cp + c] - v.omega[(size_t)i * Cp + c] * xb;
+                one = 1.0;
+                if (dbg.enabled && dbg.out.eta_b && c < v.C) dbg.out.eta_b[(size_t)c * n + i] = bi;
+            }
+            r1[slot] = bi;
+            r2[slot] = one;
+        }
+    };
+    for (int i = 0; i <= w; i++) load_row(i);
+    __syncthreads();
+
+    // ---- factorisation + fused forward substitution ----
+    const int npairs = w * (w + 1) / 2;
+    for (int j = 0; j < n; j++) {
+        const int jm = j % W1;
+        const double piv = Wn[jm * W1 + jm];
+        if (!(piv > 0.0)) {
+            if (tid == 0) {
+                v.status[c] = 1;
+                if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+            }
+            return;
+        }
+        const double dj = sqrt(piv), inv = 1.0 / dj;
+        for (int e = tid; e < W1; e += T) {
+            int slot = jm + e;
+            if (slot >= W1) slot -= W1;
+            const double le = (e == 0) ? dj : Wn[slot * W1 + jm] * inv;
+            col[e] = le;
+            Lc[(size_t)j * W1 + e] = le;
+        }
+        if (tid == T - 1) {
+            const double a = r1[jm] * inv, b = r2[jm] * inv;
+            ybc[0] = a;
+            ybc[1] = b;
+            yb[j] = a;
+            y1[j] = b;
+        }
+        __syncthreads();
+        const int j1 = (jm + 1 == W1) ? 0 : jm + 1;
+        for (int t = tid; t < npairs; t += T) {
+            int si = j1 + pair_i[t], sk = j1 + pair_k[t];
+            if (si >= W1) si -= W1;
+            if (sk >= W1) sk -= W1;
+            Wn[si * W1 + sk] -= col[1 + pair_i[t]] * col[1 + pair_k[t]];
+        }
+        for (int e = 1 + tid; e <= w; e += T) {  // forward residuals of rows j+1 .. j+w
+            int slot = jm + e;
+            if (slot >= W1) slot -= W1;
+            r1[slot] -= col[e] * ybc[0];
+            r2[slot] -= col[e] * ybc[1];
+        }
+        load_row(j + W1);  // reuses slot jm: row / column j are no longer referenced
+        __syncthreads();
+    }
+    if (dbg.enabled && dbg.out.eta_chol && c < v.C)  // column-band factor [n][bw + 1]
+        for (size_t idx = tid; idx < (size_t)n * W1; idx += T) dbg.out.eta_chol[(size_t)c * n * W1 + idx] = Lc[idx];
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- backward: L' x = y_b + eps, L' zv = y_1, (debug) L' m = y_b; one warp, lanes over the band ----
+    if (tid < 32) {
+        for (int e = tid; e < 3 * W1; e += 32) xr[e] = 0.0;
+        __syncwarp();
+        for (int j = n - 1; j >= 0; j--) {
+            const int jm = j % W1;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int e = 1 + tid; e <= w; e += 32) {
+                if (j + e < n) {
+                    const double l = Lc[(size_t)j * W1 + e];
+                    int slot = jm + e;
+                    if (slot >= W1) slot -= W1;
+                    s0 += l * xr[slot];
+                    s1 += l * xr[W1 + slot];
+                    s2 += l * xr[2 * W1 + slot];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (tid == 0) {
+                double ez;
+                if (dbg.normals) {
+                    ez = dbg.normals[(size_t)cr * (n + p + r) + j];
+                } else {
+                    Philox g;
+                    g.init(v.seed, gc, (uint32_t)j, iter, ST_NORMALS);
+                    ez = g.normal_d();
+                }
+                const double inv = 1.0 / Lc[(size_t)j * W1];
+                const double x = (yb[j] + ez - s0) * inv, z = (y1[j] - s1) * inv, m = (yb[j] - s2) * inv;
+                xr[jm] = x;
+                xr[W1 + jm] = z;
+                xr[2 * W1 + jm] = m;
+                xs[j] = x;
+                zs[j] = z;
+                ms[j] = m;
+            }
+            __syncwarp();
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- eta = x - (sum x / sum zv) zv (distributions.pyx:24-39); beta system (logit.py:226-231) ----
+    double sx = 0.0, sz = 0.0;
+    for (int i = tid; i < n; i += T) {
+        sx += xs[i];
+        sz += zs[i];
+    }
+    sx = block_sum_128(sx, red, tid);
+    sz = block_sum_128(sz, red, tid);
+    const double shift = -sx / sz;
+    for (int i = tid; i < n; i += T) {
+        const double e = xs[i] + shift * zs[i];
+        xs[i] = e;
+        v.eta_n[(size_t)i * Cp + c] = e;
+        if (dbg.enabled && dbg.out.eta_mean && c < v.C) dbg.out.eta_mean[(size_t)c * n + i] = ms[i];
+    }
+    __syncthreads();
+    for (int idx = 0; idx < p * p; idx++) {  // A = X' Om X + b_prec
+        const int a = idx / p, b = idx - a * p;
+        if (b > a) continue;
+        double s = 0.0;
+        for (int i = tid; i < n; i += T) s += v.omega[(size_t)i * Cp + c] * v.X[(size_t)i * p + a] * v.X[(size_t)i * p + b];
+        s = block_sum_128(s, red, tid);
+        if (tid == 0) {
+            small_S[a * p + b] = s + hp->b_prec[a * p + b];
+            small_S[b * p + a] = s + hp->b_prec[b * p + a];
+        }
+    }
+    for (int a = 0; a < p; a++) {  // b = X'(k - omega * eta) + b_prec b_mu
+        double s = 0.0;
+        for (int i = tid; i < n; i += T)
+            s += v.X[(size_t)i * p + a] * (v.kd[(size_t)i * Cp + c] - v.omega[(size_t)i * Cp + c] * xs[i]);
+        s = block_sum_128(s, red, tid);
+        if (tid == 0) small_b[a] = s + hp->b_pm[a];
+    }
+    __syncthreads();
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.beta_prec)
+            for (int idx = tid; idx < p * p; idx += T) dbg.out.beta_prec[(size_t)c * p * p + idx] = small_S[idx];
+        if (dbg.out.beta_b)
+            for (int a = tid; a < p; a += T) dbg.out.beta_b[(size_t)c * p + a] = small_b[a];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (small_precision_mvnorm(small_S, p, small_b, nrm, small_x, small_t)) {
+            for (int a = 0; a < p; a++) beta_s[a] = small_x[a];
+        } else {
+            ok_flag = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- alpha | . (logit.py:219-224) ----
+    const int NA = r * (r + 1) / 2;
+    for (int idx = tid; idx < r * r; idx += T) {
+        const int a = idx / r, b = idx - a * r;
+        const int k = (b <= a) ? tri(a, b) : tri(b, a);
+        small_S[idx] = v.asum[(size_t)k * Cp + c] + hp->a_prec[idx];
+    }
+    for (int a = tid; a < r; a += T) small_b[a] = v.asum[(size_t)(NA + a) * Cp + c] + hp->a_pm[a];
+    __syncthreads();
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.alpha_prec)
+            for (int idx = tid; idx < r * r; idx += T) dbg.out.alpha_prec[(size_t)c * r * r + idx] = small_S[idx];
+        if (dbg.out.alpha_b)
+            for (int a = tid; a < r; a += T) dbg.out.alpha_b[(size_t)c * r + a] = small_b[a];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (!small_precision_mvnorm(small_S, r, small_b, nrm + p, small_x, small_t)) ok_flag = 0;
+    }
+    __syncthreads();
+    if (!ok_flag) {
+        if (tid == 0) {
+            v.status[c] = 1;
+            if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+        }
+        return;
+    }
+    for (int a = tid; a < p; a += T) v.theta[(size_t)a * Cp + c] = beta_s[a];
+    for (int a = tid; a < r; a += T) v.alpha[(size_t)a * Cp + c] = small_x[a];
+    if (tid == 0) v.tau[c] = tau;
+    if (rec_alpha && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+        const size_t row = (size_t)c * rec_capacity + rec_index;
+        for (int a = tid; a < r; a += T) rec_alpha[row * r + a] = small_x[a];
+        for (int a = tid; a < p; a += T) rec_beta[row * p + a] = beta_s[a];
+        if (tid == 0) rec_tau[row] = tau;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side drivers
 // ------------------------------------------------------------------------------------------------
 template <typename PGT>
@@ -1065,6 +1420,13 @@ static void launch_alpha_injected(occu_engine* e, const double* omega_a, cudaStr
 
 static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
+    if (v.model == OCCU_LOGIT_ICAR) {
+        const size_t total = (size_t)v.n * v.Cp;
+        psi_icar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
+        e->launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     dgemm::Args a;
     memset(&a, 0, sizeof(a));
     a.A1 = v.UT; a.B = v.theta; a.Out = v.psi;
@@ -1086,6 +1448,11 @@ static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     CUDA_OK(dgemm::launch(a, st));
     e->launches++;
     return 0;
+}
+
+static size_t icar_smem_bytes(const View& v) {
+    const size_t W1 = v.bw + 1;
+    return (W1 * W1 + 6 * W1 + 2 * MAX_SMALL + 8) * sizeof(double) + (size_t)v.bw * (v.bw + 1) + 16;
 }
 
 static size_t solve_smem_bytes(const View& v) {
@@ -1114,12 +1481,25 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
                                 cudaStream_t st) {
     const View& v = e->v;
     PROF_MARK(e, KC_GRAM_GEMM, st);
-    if (launch_gram_gemm(e, st)) return -1;
+    if (v.model != OCCU_LOGIT_ICAR && launch_gram_gemm(e, st)) return -1;
     PROF_MARK(e, KC_REDUCE, st);
     const size_t per = (size_t)v.NV * v.Cp;
     reduce_partials_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(v);
     e->launches++;
     PROF_MARK(e, KC_SOLVE, st);
+    if (v.model == OCCU_LOGIT_ICAR) {
+        const size_t smem_i = icar_smem_bytes(v);
+        static size_t configured_i = 0;
+        if (smem_i > configured_i) {
+            CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+            configured_i = smem_i;
+        }
+        solve_logit_icar_kernel<<<v.Cp, ICAR_THREADS, smem_i, st>>>(v, dbg, ra, rb, rt, cap);
+        e->launches++;
+        PROF_MARK(e, KC_COUNT, st);
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = solve_smem_bytes(v);
     static size_t configured = 0;
     if (smem > configured) {
@@ -1157,8 +1537,10 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     carve(v, nullptr, &need, P->debug);
     if (!workspace || workspace_bytes < need) return set_err("workspace too small");
     if ((uintptr_t)workspace % 256) return set_err("workspace must be 256-byte aligned");
-    if (!P->X || !P->K || !P->Qrsr || !P->W || !P->y || !P->visit_ptr || !P->site_class)
-        return set_err("null problem array");
+    const bool icar = P->model == OCCU_LOGIT_ICAR;
+    if (!P->X || !P->W || !P->y || !P->visit_ptr || !P->site_class) return set_err("null problem array");
+    if (!icar && (!P->K || !P->Qrsr)) return set_err("RSR models need K and Qrsr");
+    if (icar && !P->Qband) return set_err("ICAR model needs Qband");
     if (!P->a_mu || !P->a_prec || !P->b_mu || !P->b_prec) return set_err("null hyper-parameter array");
     carve(v, (char*)workspace, &need, P->debug);
 
@@ -1211,9 +1593,14 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     FAIL_IF(cudaMemcpyAsync((void*)v.y, P->y, (size_t)v.V, cudaMemcpyDeviceToDevice, st));
     FAIL_IF(cudaMemcpyAsync((void*)v.visit_ptr, P->visit_ptr, ((size_t)v.n + 1) * 4, cudaMemcpyDeviceToDevice, st));
     FAIL_IF(cudaMemcpyAsync((void*)v.site_class, P->site_class, (size_t)v.n, cudaMemcpyDeviceToDevice, st));
-    FAIL_IF(cudaMemcpyAsync((void*)v.Qrsr, P->Qrsr, (size_t)v.q * v.q * 8, cudaMemcpyDeviceToDevice, st));
-    build_design_kernel<<<v.n, 128, v.pq * sizeof(double), st>>>(v, P->X, P->K);
-    e->launches++;
+    if (icar) {
+        FAIL_IF(cudaMemcpyAsync((void*)v.X, P->X, (size_t)v.n * v.p * 8, cudaMemcpyDeviceToDevice, st));
+        FAIL_IF(cudaMemcpyAsync((void*)v.Qband, P->Qband, (size_t)v.n * (v.bw + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        FAIL_IF(cudaMemcpyAsync((void*)v.Qrsr, P->Qrsr, (size_t)v.q * v.q * 8, cudaMemcpyDeviceToDevice, st));
+        build_design_kernel<<<v.n, 128, v.pq * sizeof(double), st>>>(v, P->X, P->K);
+        e->launches++;
+    }
     if (v.model == OCCU_PROBIT_RSR) {
         gram_unit_kernel<<<(v.M + 127) / 128, 128, 0, st>>>(v);
         e->launches++;
@@ -1258,7 +1645,9 @@ static int field_info(const occu_engine* e, int field, void** ptr, int* d, int* 
     switch (field) {
         case OCCU_F_ALPHA: *ptr = v.alpha; *d = v.r; return 0;
         case OCCU_F_BETA: *ptr = v.theta; *d = v.p; return 0;
-        case OCCU_F_ETA: *ptr = v.theta + (size_t)v.p * v.Cp; *d = v.q; return 0;
+        case OCCU_F_ETA:
+            if (v.model == OCCU_LOGIT_ICAR) { *ptr = v.eta_n; *d = v.n; return 0; }
+            *ptr = v.theta + (size_t)v.p * v.Cp; *d = v.q; return 0;
         case OCCU_F_TAU: *ptr = v.tau; *d = 1; return 0;
         case OCCU_F_Z: *ptr = v.z; *d = v.n; *is_u8 = 1; return 0;
         case OCCU_F_OMEGA: *ptr = v.omega; *d = v.n; return 0;

@@ -49,6 +49,7 @@ class DeviceEngine:
         self.V, self.r = W_rows.shape
         self.q = int(problem['K'].shape[1]) if problem.get('K') is not None else 0
         self.eta_dim = self.q if self.q else self.n
+        self.icar_bw = int(problem.get('icar_bw', 0))
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
             dev = {}
@@ -179,11 +180,16 @@ class DeviceEngine:
                     return None
                 a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), shape), order='C', copy=True)
                 return torch.from_numpy(a).to(self.device)
-            tn, tt, to = dev(normals, (C_, q + p + r)), dev(tau, (C_,)), dev(omega_a, (C_, self.V))
-            shapes = dict(eta_prec=(C_, q, q), eta_b=(C_, q), eta_chol=(C_, q, q), eta_mean=(C_, q),
-                          beta_prec=(C_, p, p), beta_b=(C_, p), alpha_prec=(C_, r, r), alpha_b=(C_, r), tau_rate=(C_,))
+            d = self.eta_dim
+            tn, tt, to = dev(normals, (C_, d + p + r)), dev(tau, (C_,)), dev(omega_a, (C_, self.V))
+            if q:
+                eta_shapes = dict(eta_prec=(C_, q, q), eta_chol=(C_, q, q))
+            else:  # ICAR: Lambda is banded; the factor comes back in column-band form, Lambda itself is not dumped
+                eta_shapes = dict(eta_prec=(1,), eta_chol=(C_, d, self.icar_bw + 1))
+            shapes = dict(eta_b=(C_, d), eta_mean=(C_, d), beta_prec=(C_, p, p), beta_b=(C_, p),
+                          alpha_prec=(C_, r, r), alpha_b=(C_, r), tau_rate=(C_,), **eta_shapes)
             bufs = {k: torch.zeros(s, dtype=torch.float64, device=self.device) for k, s in shapes.items()}
-            out = _lib.DebugOut(**{k: t.data_ptr() for k, t in bufs.items()})
+            out = _lib.DebugOut(**{k: (t.data_ptr() if (q or k != 'eta_prec') else None) for k, t in bufs.items()})
             fails = _lib.check(self.lib.occu_debug_gaussian_half(
                 self.handle, None if tn is None else tn.data_ptr(), None if tt is None else tt.data_ptr(),
                 None if to is None else to.data_ptr(), C.byref(out), self.stream.cuda_stream), 'occu_debug_gaussian_half')

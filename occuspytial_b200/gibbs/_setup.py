@@ -114,3 +114,37 @@ def verify_singular(Q):
         smallest = eigsh(Qs, k=1, sigma=-1e-6, which='LM', return_eigenvectors=False)[0]
     if smallest >= 1e-4:
         raise ValueError('Spatial precision matrix Q must be singular.')
+
+
+def band_order(Q, reorder=True):
+    """Site ordering that keeps the band of Q narrow: reverse Cuthill-McKee if it beats the given order.
+
+    Returns (perm, half_bandwidth) with new site j = old site perm[j].  This is the one-off symbolic
+    analysis of the ICAR precision: the sparsity pattern of tau Q + diag(omega) never changes, so the banded
+    Cholesky of every chain and iteration reuses it.
+    """
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    Qc = sparse.csr_matrix(Q)
+    n = Qc.shape[0]
+
+    def half_bandwidth(M):
+        coo = M.tocoo()
+        return int(np.abs(coo.row - coo.col).max()) if coo.nnz else 0
+
+    ident = np.arange(n)
+    bw0 = half_bandwidth(Qc)
+    if not reorder:
+        return ident, bw0
+    perm = np.asarray(reverse_cuthill_mckee(Qc, symmetric_mode=True), dtype=np.int64)
+    bw1 = half_bandwidth(Qc[perm][:, perm])
+    return (perm, bw1) if bw1 < bw0 else (ident, bw0)
+
+
+def lower_band(Q, perm, bw):
+    """Qband[i][d] = Q'[i][i - d] for the permuted matrix Q' = Q[perm][:, perm], d = 0..bw."""
+    Qp = sparse.csr_matrix(Q)[perm][:, perm].tocoo()
+    n = Qp.shape[0]
+    band = np.zeros((n, bw + 1))
+    keep = Qp.row >= Qp.col
+    band[Qp.row[keep], Qp.row[keep] - Qp.col[keep]] = Qp.data[keep]
+    return band

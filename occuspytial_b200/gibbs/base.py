@@ -141,6 +141,12 @@ class GibbsBase:
     def _start_keys(self):
         return ('alpha', 'beta', 'tau', 'eta')
 
+    def _start_to_engine(self, arrays):
+        return arrays
+
+    def _eta_from_engine(self, eta):
+        return eta
+
     def _initialize_posterior_state(self, start=None):
         """Set the host-visible state of chain 0 (kept for API compatibility, base.py:188-197)."""
         arrays = self._start_arrays(1, start)
@@ -151,6 +157,14 @@ class GibbsBase:
 
     def _spatial_from_eta(self, eta):
         return eta
+
+    # site-indexed arrays cross the engine boundary in the engine's site order (identity unless a
+    # subclass reorders the sites, as the ICAR sampler does to narrow the band of Q)
+    def _sites_to_engine(self, arr):
+        return arr
+
+    def _sites_from_engine(self, arr):
+        return arr
 
     # ------------------------------------------------------------------------------------------
     # engine plumbing
@@ -184,7 +198,7 @@ class GibbsBase:
             start = self._initialize_posterior_state(None)
             seed = int(self.rng.integers(0, 2**63 - 1))
             self._engine = self._make_engine(1, seed)
-            self._engine.set_start(start)
+            self._engine.set_start(self._start_to_engine(start))
         self._engine.sweep(1)
         self._pull_state(self._engine)
 
@@ -193,10 +207,10 @@ class GibbsBase:
         self.state.alpha = engine.get_field(_lib.F_ALPHA)[0]
         self.state.beta = engine.get_field(_lib.F_BETA)[0]
         self.state.tau = float(engine.get_field(_lib.F_TAU)[0])
-        self.state.eta = engine.get_field(_lib.F_ETA)[0]
+        self.state.eta = self._eta_from_engine(engine.get_field(_lib.F_ETA)[0])
         self.state.spatial = self._spatial_from_eta(self.state.eta)
         if engine.chains <= 64:
-            self.state.z = engine.get_field(_lib.F_Z)[0].astype(np.float64)
+            self.state.z = self._sites_from_engine(engine.get_field(_lib.F_Z)[0].astype(np.float64))
             self.state.k = self.state.z - 0.5
 
     def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None,
@@ -221,7 +235,7 @@ class GibbsBase:
         arrays = {k: v[lo:hi] for k, v in arrays.items()}
         engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64)
         try:
-            engine.set_start(arrays)
+            engine.set_start(self._start_to_engine(arrays))
             draws = size - burnin
             dims = {'alpha': engine.r, 'beta': engine.p, 'tau': 1}
             per_draw = 8 * local * sum(dims.values())

@@ -26,6 +26,45 @@ class LogitICARGibbs(GibbsBase):
 
     def _configure(self, Q, hparams):
         super()._configure(Q, hparams)
+        self._perm = None   # symbolic analysis (band ordering) is done lazily, only the ICAR engine needs it
+
+    # ---- engine boundary: the ICAR engine works in a bandwidth-reducing site order ----
+    def _band(self):
+        if self._perm is None:
+            self._perm, self._bw = _setup.band_order(self.fixed.Q)
+            self._inv = np.empty_like(self._perm)
+            self._inv[self._perm] = np.arange(self._perm.size)
+        return self._perm, self._bw
+
+    def _sites_to_engine(self, arr):
+        perm, _ = self._band()
+        return np.ascontiguousarray(np.asarray(arr)[..., perm])
+
+    def _sites_from_engine(self, arr):
+        self._band()
+        return np.ascontiguousarray(np.asarray(arr)[..., self._inv])
+
+    def _start_to_engine(self, arrays):
+        out = dict(arrays)
+        out['eta'] = self._sites_to_engine(arrays['eta'])
+        return out
+
+    def _eta_from_engine(self, eta):
+        return self._sites_from_engine(eta)
+
+    def _problem_arrays(self):
+        from ..data import Data
+        perm, bw = self._band()
+        f = self.fixed
+        n = f.n
+        inv = self._inv
+        W_rows, visit_ptr = Data({int(inv[s]): self.W[s] for s in self.W.surveyed}).to_csr(n)
+        y_rows, _ = Data({int(inv[s]): self.y[s] for s in self.y.surveyed}).to_csr(n, dtype=np.uint8)
+        return dict(X=np.ascontiguousarray(self.X[perm]), W_rows=W_rows.reshape(W_rows.shape[0], -1), y_rows=y_rows,
+                    visit_ptr=visit_ptr, site_class=np.ascontiguousarray(f.site_class[perm]),
+                    Qband=_setup.lower_band(f.Q, perm, bw), icar_bw=bw,
+                    tau_rate=f.tau_rate, tau_shape=f.tau_shape,
+                    a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
 
 
 class LogitRSRGibbs(LogitICARGibbs):
@@ -65,8 +104,21 @@ class LogitRSRGibbs(LogitICARGibbs):
     def _spatial_from_eta(self, eta):
         return self.fixed.K @ eta
 
+    # the RSR engine keeps the natural site order
+    def _sites_to_engine(self, arr):
+        return arr
+
+    def _sites_from_engine(self, arr):
+        return arr
+
+    def _start_to_engine(self, arrays):
+        return arrays
+
+    def _eta_from_engine(self, eta):
+        return eta
+
     def _problem_arrays(self):
-        prob = super()._problem_arrays()
+        prob = GibbsBase._problem_arrays(self)
         prob['K'] = self.fixed.K
         prob['Qrsr'] = self.fixed.Q
         return prob
