@@ -146,3 +146,18 @@ def test_gemm_tn_vs_torch_fp64(env):
         ref = A.T @ B
         err = (out - ref).abs().max().item() / ref.abs().max().item()
         assert err < 1e-13, (M, N, K, err)
+
+
+def test_chain_summaries_kernel_vs_host(env):
+    """Per-chain summary blocks (the payload of the NCCL all-gather) against the NumPy definition."""
+    torch, lib, _lib = env
+    from occuspytial_b200.diagnostics import summaries_from_draws
+    rng = np.random.default_rng(4)
+    chains, draws, dim, L = 37, 501, 3, 40
+    rec = np.cumsum(rng.normal(size=(chains, draws, dim)), axis=1) * 0.05 + rng.normal(size=(chains, draws, dim))
+    t = torch.from_numpy(rec).cuda()
+    out = torch.empty((chains, dim, 6 + L + 1), dtype=torch.float64, device='cuda')
+    _lib.check(lib.occu_chain_summaries(t.data_ptr(), chains, draws, dim, L, out.data_ptr(), None), 'summaries')
+    got = out.cpu().numpy()
+    for k in range(dim):
+        np.testing.assert_allclose(got[:, k], summaries_from_draws(rec[:, :, k], L), rtol=1e-10, atol=1e-12)
