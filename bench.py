@@ -28,8 +28,8 @@ METRIC = 'chain-iterations/sec, LogitRSRGibbs n=10k sites, 4096 chains, 1/2/4/8 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--lattice', default='100x100')
     ap.add_argument('--q', type=int, default=64)
@@ -94,14 +94,16 @@ def run_reference(args):
     wl = workload(args)
     cores = os.cpu_count()
     # a "step" of this arm = one Gibbs iteration of `cores` concurrent chains (bounded sample of the workload)
-    value, elapsed = cpu_chain_iters_per_sec(wl, cores, args.warmup, args.steps)
+    # the CPU arm needs ~60 ms per chain-iteration: bound the sample so that the default run ends in minutes
+    steps, warm = min(args.steps, 100), min(args.warmup, 10)
+    value, elapsed = cpu_chain_iters_per_sec(wl, cores, warm, steps)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * elapsed / steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': config_dict(args, wl),
         'cpu_baseline': {'value': value, 'unit': 'chain-iterations/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{cores} chains x {args.steps} iterations of the same n={wl["n"]}, q={wl["q"]} '
+                         'sample': f'{cores} chains x {steps} iterations of the same n={wl["n"]}, q={wl["q"]} '
                                    'workload, one process per chain (oracle/sweep.py + oracle/pg_devroye.c: NumPy/'
                                    'LAPACK restatement of the reference sweep; the Python reference itself cannot '
                                    'travel to the GPU box and needs the absent polyagamma package)'},

@@ -224,6 +224,9 @@ class GibbsBase:
         if self._model is None:
             raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
         rank, world = dist_info()
+        if device is None and world > 1:
+            import os
+            device = f"cuda:{os.environ.get('LOCAL_RANK', rank)}"   # one process per GPU under torchrun
         # the same host RNG stream is consumed on every rank: start values and the device seed are
         # generated for ALL chains and sliced, so that sharding never changes a chain
         seed = int(self.rng.integers(0, 2**63 - 1))
