@@ -34,7 +34,7 @@ def parse():
     ap.add_argument('--lattice', default='100x100')
     ap.add_argument('--q', type=int, default=64)
     ap.add_argument('--chains', type=int, default=4096, help='chains per GPU')
-    ap.add_argument('--cpu-iters', type=int, default=60, help='iterations per CPU-baseline chain')
+    ap.add_argument('--cpu-iters', type=int, default=300, help='iterations per CPU-baseline chain')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--pg-fp64', action='store_true')
@@ -64,18 +64,20 @@ def config_dict(args, wl):
 # CPU arm: the oracle port of the reference's sweep, one process per chain over all host cores
 # --------------------------------------------------------------------------------------------------
 def _cpu_worker(payload):
-    os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    os.environ['OMP_NUM_THREADS'] = '1'
+    # one BLAS thread per chain process, as the reference's loky workers are meant to run;
+    # the environment variables are too late once NumPy is loaded, so the pools are limited at run time
+    from threadpoolctl import threadpool_limits
     from oracle import sweep as S
     wl, seed, warm, iters = payload
-    s = S.OracleSampler('logit_rsr', wl['Q'], wl['W'], wl['X'], wl['y'], seed=seed, K=wl['K'])
-    s.init_state()
-    for _ in range(warm):
-        s.step()
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        s.step()
-    return time.perf_counter() - t0
+    with threadpool_limits(limits=1):
+        s = S.OracleSampler('logit_rsr', wl['Q'], wl['W'], wl['X'], wl['y'], seed=seed, K=wl['K'])
+        s.init_state()
+        for _ in range(warm):
+            s.step()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            s.step()
+        return time.perf_counter() - t0
 
 
 def cpu_chain_iters_per_sec(wl, cores, warm, iters):

@@ -167,9 +167,13 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     }
     v.n_tiles = (P->n + SITE_TILE - 1) / SITE_TILE;
     v.NV = P->r * (P->r + 1) / 2 + P->r;
-    // solve kernel keeps the packed joint Gram + H + a few vectors in shared memory
-    const size_t solve_smem = ((size_t)v.M + 6 * (size_t)v.pq + 64) * 8;
-    if (solve_smem > 220 * 1024) return set_err("p + q too large for the shared-memory solve (p+q <= ~230)");
+    // solve kernel keeps Lambda (4x4-blocked, packed lower triangle) and a few vectors in shared memory
+    if (!icar) {
+        const size_t qb = (v.q + 3) / 4;
+        const size_t solve_smem = ((qb + 1) * (qb + 2) / 2 * 17 + 4 * qb * (v.p + 3) + (size_t)v.p * v.p + 2 * v.pq + 128) * 8;
+        if (solve_smem > 200 * 1024) return set_err("RSR rank q too large for the shared-memory solve (q <= ~200)");
+        if (qb > 254) return set_err("RSR rank q too large");
+    }
     return 0;
 }
 
@@ -667,20 +671,62 @@ __device__ bool small_precision_mvnorm(double* S, int d, const double* b, const 
     return true;
 }
 
+// ---- 4x4-blocked Cholesky machinery of the RSR solve ------------------------------------------------
+// Lambda (q x q, padded to qb = ceil(q/4) blocks with an identity tail) plus ONE extra block row holding the
+// right-hand side b (row 0 of block row qb) are kept in shared memory as packed lower-triangular 4x4 blocks,
+// block (I, K) at BLK * (I (I + 1) / 2 + K), row-major inside, BLK = 17 doubles (odd stride: threads working on
+// consecutive blocks hit different banks).  Factorising the augmented matrix yields y = L^-1 b in the extra
+// row for free.  Per block column J: (1) every thread that owns a panel block (I, J) factorises the 4x4
+// diagonal block redundantly in registers and solves its own block against it -- no serial section, no extra
+// barrier; (2) the trailing blocks (I, K), J < K <= I, are updated by A_IK -= P_I P_K' (64 FMAs per block).
+// Two barriers per block column instead of three per column, and no per-element index decoding.
+constexpr int BLK = 17;
+__device__ __forceinline__ int bidx(int I, int K) { return (I * (I + 1) / 2 + K) * BLK; }
+
+// lower Cholesky of a 4x4 block held in registers (a[r][c], c <= r used); returns false on a bad pivot
+__device__ __forceinline__ bool chol4(double (&a)[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double d = a[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= a[j][k] * a[j][k];
+        if (!(d > 0.0)) return false;
+        const double dj = sqrt(d), inv = 1.0 / dj;
+        a[j][j] = dj;
+#pragma unroll
+        for (int i = j + 1; i < 4; i++) {
+            double t = a[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) t -= a[i][k] * a[j][k];
+            a[i][j] = t * inv;
+        }
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
                                                                          double* rec_alpha, double* rec_beta,
                                                                          double* rec_tau, int rec_capacity) {
     extern __shared__ double sm[];
     const int c = blockIdx.x, tid = threadIdx.x, T = SOLVE_THREADS;
-    const int p = v.p, q = v.q, r = v.r, pq = v.pq, M = v.M;
+    const int p = v.p, q = v.q, r = v.r, pq = v.pq;
+    const int qb = (q + 3) / 4, q4 = qb * 4;
+    const int nblk = (qb + 1) * (qb + 2) / 2;  // lower-triangular blocks incl. the right-hand-side block row
     const size_t Cp = v.Cp;
     const HParams* hp = v.hp;
-    double* Gs = sm;             // [M] packed lower triangle of the joint Gram over [beta; eta]
-    double* h = Gs + M;          // [pq]  U'(z - 1/2)
-    double* th = h + pq;         // [pq]  current beta, eta
-    double* rhs = th + pq;       // [2*pq] two right-hand sides
-    double* nrm = rhs + 2 * pq;  // [pq + r] normals
-    double* red = nrm + pq + MAX_SMALL;  // [T/32 + 2] reduction scratch
+    double* Bs = sm;                          // [nblk][BLK]
+    double* gx = Bs + (size_t)nblk * BLK;     // [q4][p]  K' Om X  (rows of the joint Gram below the XX block)
+    double* gxx = gx + (size_t)q4 * p;        // [p][p]   X' Om X (symmetric, full)
+    double* h = gxx + p * p;                  // [pq]     U'(z - 1/2)
+    double* th = h + pq;                      // [pq + 4] current beta, eta (eta padded)
+    double* xm = th + pq + 4;                 // [q4] backward-solve result: mean
+    double* xe = xm + q4;                     // [q4] backward-solve result: L^-T eps
+    double* nrm = xe + q4;                    // [q4 + p + r] normals (eta part padded to q4)
+    double* red = nrm + q4 + 2 * MAX_SMALL;   // [8]
+    double* Ld = red + 8;                     // [qb][16] factored diagonal blocks (kept apart: the panel threads
+                                              //          read the unfactored block while its owner factorises it)
+    uint8_t* pair_i = reinterpret_cast<uint8_t*>(Ld + qb * 16);
+    uint8_t* pair_k = pair_i + nblk;
     __shared__ double small_S[MAX_SMALL * MAX_SMALL];
     __shared__ double small_b[MAX_SMALL], small_x[MAX_SMALL], small_t[MAX_SMALL];
     __shared__ int ok_flag;
@@ -692,24 +738,37 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
 
     // logit: per-chain omega-weighted Gram; probit: the shared unit-weight Gram (A_eta = K'K + tau Q, probit.py:226)
     const double* Grow = v.model == OCCU_PROBIT_RSR ? v.G0 : v.G + (size_t)c * v.M_pad;
-    for (int m = tid; m < M; m += T) Gs[m] = Grow[m];
+
     for (int a = tid; a < pq; a += T) {
         double hs = 0.0;  // K-split partials, fixed order
         for (int s = 0; s < v.ksplit; s++) hs += v.Hpart[((size_t)s * Cp + c) * v.ldh + a];
         h[a] = hs;
         th[a] = v.theta[(size_t)a * Cp + c];
     }
-    // normals: eta (q), beta (p), alpha (r)
-    for (int k = tid; k < pq + r; k += T) {
-        double val;
-        if (dbg.normals) {
-            val = dbg.normals[(size_t)cr * (pq + r) + k];
-        } else {
-            Philox g;
-            g.init(v.seed, gc, (uint32_t)k, iter, ST_NORMALS);
-            val = g.normal_d();
+    // normals: eta (q), beta (p), alpha (r); stored as eta[0..q4) (zero padded), then beta, alpha
+    for (int k = tid; k < q4 + p + r; k += T) {
+        const int src = k < q4 ? k : k - q4 + q;  // index in the (q + p + r) stream
+        double val = 0.0;
+        if (k >= q4 || k < q) {
+            if (dbg.normals) {
+                val = dbg.normals[(size_t)cr * (pq + r) + src];
+            } else {
+                Philox g;
+                g.init(v.seed, gc, (uint32_t)src, iter, ST_NORMALS);
+                val = g.normal_d();
+            }
         }
         nrm[k] = val;
+    }
+    {   // block-pair table: t -> (ii, kk), kk <= ii, row-major over the lower triangle
+        int t = 0;
+        for (int ii = 0; ii <= qb; ii++) {
+            for (int kk = tid; kk <= ii; kk += T) {
+                pair_i[t + kk] = (uint8_t)ii;
+                pair_k[t + kk] = (uint8_t)kk;
+            }
+            t += ii + 1;
+        }
     }
     if (tid == 0) ok_flag = 1;
     __syncthreads();
@@ -744,28 +803,102 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     }
     const double tau = red[T / 32];
 
-    // ---- eta | .   Lambda = K' Om K + tau Qrsr,  b = K'k - (K' Om X) beta   (logit.py:478-485, 327-336) ----
-    for (int idx = tid; idx < q * q; idx += T) {
-        const int i = idx / q, j = idx - i * q;
-        if (j <= i) Gs[tri(p + i, p + j)] += tau * v.Qrsr[idx];
+    // ---- stage the joint Gram: XX block, KX rows, and Lambda = K' Om K + tau Qrsr in blocked form ----
+    for (int idx = tid; idx < nblk * BLK; idx += T) Bs[idx] = 0.0;
+    for (int idx = tid; idx < p * p; idx += T) {
+        const int a = idx / p, b = idx - a * p;
+        gxx[idx] = (b <= a) ? Grow[tri(a, b)] : Grow[tri(b, a)];
     }
-    for (int i = tid; i < q; i += T) {
-        double b = h[p + i];
-        for (int a = 0; a < p; a++) b -= Gs[tri(p + i, a)] * th[a];
-        rhs[i] = b;
+    for (int idx = tid; idx < q4 * p; idx += T) {
+        const int i = idx / p, a = idx - i * p;
+        gx[idx] = i < q ? Grow[tri(p + i, a)] : 0.0;
     }
     __syncthreads();
-    if (dbg.enabled && c < v.C) {
-        if (dbg.out.eta_prec)
-            for (int idx = tid; idx < q * q; idx += T) {
-                const int i = idx / q, j = idx - i * q;
-                dbg.out.eta_prec[(size_t)c * q * q + idx] = (j <= i) ? Gs[tri(p + i, p + j)] : Gs[tri(p + j, p + i)];
-            }
-        if (dbg.out.eta_b)
-            for (int i = tid; i < q; i += T) dbg.out.eta_b[(size_t)c * q + i] = rhs[i];
+    for (int i = 0; i < q; i++) {  // row i of Lambda: contiguous in the packed Gram
+        const double* grow = Grow + tri(p + i, p);
+        double* brow = Bs + (i & 3) * 4;
+        const int I = i >> 2;
+        for (int j = tid; j <= i; j += T)
+            brow[bidx(I, j >> 2) + (j & 3)] = grow[j] + tau * v.Qrsr[(size_t)i * q + j];
     }
-    const bool pd = block_cholesky_packed(Gs, p, q, tid, T);
-    if (!pd) {
+    for (int i = q + tid; i < q4; i += T) Bs[bidx(i >> 2, i >> 2) + (i & 3) * 5] = 1.0;  // identity padding
+    __syncthreads();
+    // right-hand side b = K'k - (K' Om X) beta  (logit.py:481) into row 0 of block row qb
+    for (int i = tid; i < q; i += T) {
+        double b = h[p + i];
+        for (int a = 0; a < p; a++) b -= gx[i * p + a] * th[a];
+        Bs[bidx(qb, i >> 2) + (i & 3)] = b;
+        if (dbg.enabled && dbg.out.eta_b && c < v.C) dbg.out.eta_b[(size_t)c * q + i] = b;
+    }
+    __syncthreads();
+    if (dbg.enabled && dbg.out.eta_prec && c < v.C)
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            const int ii = i >= j ? i : j, jj = i >= j ? j : i;
+            dbg.out.eta_prec[(size_t)c * q * q + idx] = Bs[bidx(ii >> 2, jj >> 2) + (ii & 3) * 4 + (jj & 3)];
+        }
+
+    // ---- blocked right-looking Cholesky of the augmented matrix ----
+    for (int J = 0; J < qb; J++) {
+        // (1) panel: blocks (I, J), I = J .. qb
+        for (int I = J + tid; I <= qb; I += T) {
+            double d[4][4];
+            const double* dj = Bs + bidx(J, J);
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) d[a][b] = dj[a * 4 + b];
+            if (!chol4(d)) {
+                ok_flag = 0;
+                continue;
+            }
+            double* blk = Bs + bidx(I, J);
+            if (I == J) {
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) Ld[J * 16 + a * 4 + b] = b <= a ? d[a][b] : 0.0;
+            } else {  // P = A_IJ L_JJ^-T, row by row
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    double x[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        double t = blk[a * 4 + b];
+#pragma unroll
+                        for (int k = 0; k < b; k++) t -= x[k] * d[b][k];
+                        x[b] = t / d[b][b];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; b++) blk[a * 4 + b] = x[b];
+                }
+            }
+        }
+        __syncthreads();
+        if (!ok_flag) break;
+        // (2) trailing update: blocks (J+1+ii, J+1+kk), kk <= ii <= qb-J-1
+        const int m1 = qb - J;  // block rows below J, including the right-hand-side row
+        const int cnt = m1 * (m1 + 1) / 2;
+        for (int t = tid; t < cnt; t += T) {
+            const int I = J + 1 + pair_i[t], K = J + 1 + pair_k[t];
+            if (K > qb - 1 + (I == qb ? 0 : 1)) continue;  // (qb, qb) does not exist
+            const double* PI = Bs + bidx(I, J);
+            const double* PK = Bs + bidx(K, J);
+            double* A = Bs + bidx(I, K);
+            double pk[4][4];
+#pragma unroll
+            for (int e = 0; e < 16; e++) pk[e >> 2][e & 3] = PK[e];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const double p0 = PI[a * 4], p1 = PI[a * 4 + 1], p2 = PI[a * 4 + 2], p3 = PI[a * 4 + 3];
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    A[a * 4 + b] -= p0 * pk[b][0] + p1 * pk[b][1] + p2 * pk[b][2] + p3 * pk[b][3];
+            }
+        }
+        __syncthreads();
+    }
+    if (!ok_flag) {
         if (tid == 0) {
             v.status[c] = 1;
             if (c < v.C) atomicAdd(&v.ctl->fails, 1);
@@ -775,53 +908,68 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     if (dbg.enabled && dbg.out.eta_chol && c < v.C)
         for (int idx = tid; idx < q * q; idx += T) {
             const int i = idx / q, j = idx - i * q;
-            dbg.out.eta_chol[(size_t)c * q * q + idx] = (j <= i) ? Gs[tri(p + i, p + j)] : 0.0;
+            const int I = i >> 2, K = j >> 2, e = (i & 3) * 4 + (j & 3);
+            dbg.out.eta_chol[(size_t)c * q * q + idx] = (j <= i) ? (I == K ? Ld[I * 16 + e] : Bs[bidx(I, K) + e]) : 0.0;
         }
-    // forward: L y = b (column sweep)
-    for (int j = 0; j < q; j++) {
-        __syncthreads();
-        const double yj = rhs[j] / Gs[tri(p + j, p + j)];
-        __syncthreads();
-        if (tid == 0) rhs[j] = yj;
-        for (int i = j + 1 + tid; i < q; i += T) rhs[i] -= Gs[tri(p + i, p + j)] * yj;
+
+    // ---- backward, right-looking over block rows: L' m = y (mean) and L' e = eps ----
+    // thread J owns the two 4-vectors of block row J
+    double rm[4] = {0, 0, 0, 0}, re[4] = {0, 0, 0, 0};
+    if (tid < qb) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            rm[b] = Bs[bidx(qb, tid) + b];  // y = L^-1 b (row 0 of the extra block row)
+            re[b] = nrm[tid * 4 + b];
+        }
     }
-    __syncthreads();
-    // backward with two right-hand sides: L' m = y (mean) and L' e = normals
-    double* rhs2 = rhs + pq;
-    for (int i = tid; i < q; i += T) rhs2[i] = nrm[i];
-    for (int j = q - 1; j >= 0; j--) {
-        __syncthreads();
-        const double d = Gs[tri(p + j, p + j)];
-        const double mj = rhs[j] / d, ej = rhs2[j] / d;
-        __syncthreads();
-        if (tid == 0) {
-            rhs[j] = mj;
-            rhs2[j] = ej;
+    for (int I = qb - 1; I >= 0; I--) {
+        if (tid == I) {  // x_I = L_II^-T rhs_I
+            const double* L = Ld + I * 16;
+#pragma unroll
+            for (int a = 3; a >= 0; a--) {
+                double tm = rm[a], te = re[a];
+#pragma unroll
+                for (int k = a + 1; k < 4; k++) {
+                    tm -= L[k * 4 + a] * rm[k];
+                    te -= L[k * 4 + a] * re[k];
+                }
+                rm[a] = tm / L[a * 4 + a];
+                re[a] = te / L[a * 4 + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                xm[I * 4 + a] = rm[a];
+                xe[I * 4 + a] = re[a];
+            }
         }
-        for (int i = tid; i < j; i += T) {
-            const double l = Gs[tri(p + j, p + i)];
-            rhs[i] -= l * mj;
-            rhs2[i] -= l * ej;
+        __syncthreads();
+        if (tid < I) {  // rhs_J -= L_IJ' x_I
+            const double* L = Bs + bidx(I, tid);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double m = xm[I * 4 + k], e = xe[I * 4 + k];
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    rm[b] -= L[k * 4 + b] * m;
+                    re[b] -= L[k * 4 + b] * e;
+                }
+            }
         }
     }
     __syncthreads();
     if (dbg.enabled && dbg.out.eta_mean && c < v.C)
-        for (int i = tid; i < q; i += T) dbg.out.eta_mean[(size_t)c * q + i] = rhs[i];
-    for (int i = tid; i < q; i += T) th[p + i] = rhs[i] + rhs2[i];  // eta = mean + L^-T eps
+        for (int i = tid; i < q; i += T) dbg.out.eta_mean[(size_t)c * q + i] = xm[i];
+    for (int i = tid; i < q; i += T) th[p + i] = xm[i] + xe[i];  // eta = mean + L^-T eps
     __syncthreads();
 
     // ---- beta | .   A = X' Om X + b_prec,  b = X'k - (X' Om K) eta + b_prec b_mu   (logit.py:226-232) ----
-    for (int idx = tid; idx < p * p; idx += T) {
-        const int a = idx / p, b = idx - a * p;
-        small_S[idx] = ((b <= a) ? Gs[tri(a, b)] : Gs[tri(b, a)]) + hp->b_prec[idx];
-    }
+    for (int idx = tid; idx < p * p; idx += T) small_S[idx] = gxx[idx] + hp->b_prec[idx];
     for (int a = tid; a < p; a += T) {
         double b = h[a] + hp->b_pm[a];
-        for (int j = 0; j < q; j++) b -= Gs[tri(p + j, a)] * th[p + j];
+        for (int j = 0; j < q; j++) b -= gx[j * p + a] * th[p + j];
         small_b[a] = b;
     }
     __syncthreads();
-    // NOTE: rows p.. of Gs columns < p are untouched by the Cholesky (it only rewrites the KK block)
     if (dbg.enabled && c < v.C) {
         if (dbg.out.beta_prec)
             for (int idx = tid; idx < p * p; idx += T) dbg.out.beta_prec[(size_t)c * p * p + idx] = small_S[idx];
@@ -830,7 +978,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     }
     __syncthreads();
     if (tid == 0) {
-        if (small_precision_mvnorm(small_S, p, small_b, nrm + q, small_x, small_t)) {
+        if (small_precision_mvnorm(small_S, p, small_b, nrm + q4, small_x, small_t)) {
             for (int a = 0; a < p; a++) th[a] = small_x[a];
         } else {
             ok_flag = 0;
@@ -855,7 +1003,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     }
     __syncthreads();
     if (tid == 0) {
-        if (!small_precision_mvnorm(small_S, r, small_b, nrm + pq, small_x, small_t)) ok_flag = 0;
+        if (!small_precision_mvnorm(small_S, r, small_b, nrm + q4 + p, small_x, small_t)) ok_flag = 0;
     }
     __syncthreads();
     if (!ok_flag) {
@@ -1456,7 +1604,10 @@ static size_t icar_smem_bytes(const View& v) {
 }
 
 static size_t solve_smem_bytes(const View& v) {
-    return ((size_t)v.M + 5 * (size_t)v.pq + MAX_SMALL + SOLVE_THREADS / 32 + 8) * sizeof(double);
+    const size_t qb = (v.q + 3) / 4, q4 = qb * 4;
+    const size_t nblk = (qb + 1) * (qb + 2) / 2;
+    const size_t doubles = nblk * 17 + q4 * v.p + (size_t)v.p * v.p + 2 * (size_t)v.pq + 4 + 3 * q4 + 2 * MAX_SMALL + 8 + qb * 16;
+    return doubles * sizeof(double) + 2 * nblk + 16;
 }
 
 #define PROF_MARK(e, k, st)                                           \

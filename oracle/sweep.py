@@ -465,9 +465,10 @@ class OracleSampler:
 
 def _run_chain(args):
     model, data, kw, seed, size, burnin = args
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
-    s = OracleSampler(model, *data, seed=seed, **kw)
-    return s.run(size, burnin)
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):   # one BLAS thread per chain process
+        s = OracleSampler(model, *data, seed=seed, **kw)
+        return s.run(size, burnin)
 
 
 def run_chains(model, Q, W, X, y, size, burnin=0, chains=2, seed=0, processes=None, **kw):
