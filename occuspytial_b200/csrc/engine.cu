@@ -45,7 +45,7 @@ static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 // Philox stage ids (ctr[3] high byte)
 enum { ST_Z = 0, ST_OMEGA_B = 1, ST_OMEGA_A = 2, ST_TAU = 3, ST_NORMALS = 4, ST_EPS = 5, ST_HOOK = 6 };
 
-constexpr int SITE_TILE = 32;    // sites per CTA in the site pass
+constexpr int SITE_TILE = 64;    // sites per CTA in the site pass (z bits of a tile live in one 64-bit register)
 constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
 constexpr int SOLVE_THREADS = 128;
 constexpr int MAX_SMALL = 32;    // max p and r
@@ -87,6 +87,7 @@ struct View {
     double* Hpart;  // [ksplit][Cp][ldh]  K-split partials of U'(z - 1/2)
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
+    double* gam;    // [Cp]  Gamma(tau_shape, 1) variates of this iteration
     double* zprob;  // [n][Cp] or NULL
     double* eps;    // [n_pad][Cp]  probit only
     // ICAR only
@@ -209,6 +210,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.Hpart = icar ? nullptr : c.take<double>((size_t)v.ksplit * Cp * v.ldh);
     v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
     v.asum = c.take<double>((size_t)v.NV * Cp);
+    v.gam = c.take<double>(Cp);
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
     v.status = c.take<int32_t>(Cp);
     *total = align_up(c.off, 256);
@@ -309,7 +311,8 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 template <int R, typename PGT>
 __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
-    __shared__ PGT arg_s[SITE_TILE][CHAIN_TILE];  // column tid is private to thread tid
+    extern __shared__ __align__(16) unsigned char site_smem[];
+    PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // column tid is private to thread tid
     const int tid = threadIdx.x;
     const int c = blockIdx.y * CHAIN_TILE + tid;
     const int tile = blockIdx.x;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
     for (int k = 0; k < R; k++) al[k] = v.alpha[(size_t)k * Cp + c];
 
     // ---- phase 1: z | . ----
-    uint32_t zbits = 0u;
+    uint64_t zbits = 0ull;
     for (int i = i0; i < i1; i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
             v.z[off] = (uint8_t)zc;
             v.kd[off] = (double)zc - 0.5;  // logit.py:252
         }
-        zbits |= (uint32_t)zc << (i - i0);
+        zbits |= (uint64_t)zc << (i - i0);
         arg_s[i - i0][tid] = (PGT)psi;
     }
 
@@ -367,41 +370,42 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
     int i = i0 - 1, vv = 0, vend = 0, cur = 0;
-    bool site_pending = false, active = true, have = false, is_visit = false;
+    bool site_done = true, active = true, have = false, is_visit = false;
     PGTask<PGT> task;
     Philox g;
     while (__any_sync(0xffffffffu, active || have)) {
         if (!have && active) {
-            for (;;) {
-                if (vv < vend) {  // omega_a ~ PG(1, w_ij alpha) (logit.py:187-193)
+            // next draw of this lane's stream, loop-free: the visits of an occupied surveyed site
+            // (omega_a ~ PG(1, w_ij alpha), logit.py:187-193), then the site itself (omega_b ~ PG(1, psi),
+            // logit.py:201-204), then the next site
+            if (vv >= vend && site_done) {
+                if (++i >= i1) {
+                    active = false;
+                } else {
+                    site_done = false;
+                    if (v.site_class[i] != OCCU_SITE_NOT_SURVEYED && ((zbits >> (i - i0)) & 1ull)) {
+                        vv = v.visit_ptr[i];
+                        vend = v.visit_ptr[i + 1];
+                    }
+                }
+            }
+            if (active) {
+                PGT carg;
+                is_visit = vv < vend;
+                if (is_visit) {
                     cur = vv++;
                     double lin = 0.0;
 #pragma unroll
                     for (int k = 0; k < R; k++) lin += v.W[(size_t)cur * R + k] * al[k];
-                    is_visit = true;
-                    g.init(v.seed, gc, (uint32_t)cur, iter, ST_OMEGA_A);
-                    pg1_setup<PGT>((PGT)lin, task);
-                    have = true;
-                    break;
-                }
-                if (site_pending) {  // omega_b ~ PG(1, psi) (logit.py:201-204)
-                    site_pending = false;
+                    carg = (PGT)lin;
+                } else {
+                    site_done = true;
                     cur = i;
-                    is_visit = false;
-                    g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
-                    pg1_setup<PGT>(arg_s[i - i0][tid], task);
-                    have = true;
-                    break;
+                    carg = arg_s[i - i0][tid];
                 }
-                if (++i >= i1) {
-                    active = false;
-                    break;
-                }
-                site_pending = true;
-                if (v.site_class[i] != OCCU_SITE_NOT_SURVEYED && ((zbits >> (i - i0)) & 1u)) {
-                    vv = v.visit_ptr[i];
-                    vend = v.visit_ptr[i + 1];
-                }
+                g.init(v.seed, gc, (uint32_t)cur, iter, is_visit ? ST_OMEGA_A : ST_OMEGA_B);
+                pg1_setup<PGT>(carg, task);   // one shared copy of the setup code for both kinds of draw
+                have = true;
             }
         }
         if (have) {
@@ -591,16 +595,6 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
 }
 
-// asum[k][c] = sum_tile apart[tile][k][c], fixed order
-__global__ void reduce_partials_kernel(const View v) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t per = (size_t)v.NV * v.Cp;
-    if (idx >= per) return;
-    double s = 0.0;
-    for (int t = 0; t < v.n_tiles; t++) s += v.apart[(size_t)t * per + idx];
-    v.asum[idx] = s;
-}
-
 // ------------------------------------------------------------------------------------------------
 // per-chain solve: tau, eta, beta, alpha
 // ------------------------------------------------------------------------------------------------
@@ -671,6 +665,68 @@ __device__ bool small_precision_mvnorm(double* S, int d, const double* b, const 
     return true;
 }
 
+// Per-chain scalar work that does not depend on the Gram, one THREAD per chain (chain-minor, coalesced):
+//  * alpha | omega_a, z  (logit.py:219-224 / probit.py:231-235), committed and recorded here,
+//  * the unit-rate Gamma variate of tau | eta (tau = gam / rate, logit.py:206-209).
+// Keeping these serial FP64 chains (sqrt / divide / log) out of the one-CTA-per-chain solve kernels matters:
+// there a single lane would hold 127 others at a barrier for ~10^4 cycles per chain.
+__global__ void __launch_bounds__(32) alpha_tau_kernel(const View v, const SolveDebug dbg, double* rec_alpha,
+                                                        int rec_capacity) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.Cp) return;
+    const int r = v.r, NA = r * (r + 1) / 2, NV = v.NV;
+    const size_t Cp = v.Cp;
+    const HParams* hp = v.hp;
+    const uint32_t iter = v.ctl->iter;
+    const int rec_index = v.ctl->rec_index;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const int cr = c % v.C;
+    const int d_eta = v.model == OCCU_LOGIT_ICAR ? v.n : v.q;   // normals stream: eta, beta, alpha
+    double sums[8 * 9 / 2 + 8];
+    for (int k = 0; k < NV; k++) sums[k] = v.asum[(size_t)k * Cp + c];  // reduced by reduce_partials_kernel
+    double S[64], b[8], x[8], tmp[8], zn[8];
+    for (int a = 0; a < r; a++) {
+        for (int bb = 0; bb < r; bb++) S[a * r + bb] = sums[bb <= a ? tri(a, bb) : tri(bb, a)] + hp->a_prec[a * r + bb];
+        b[a] = sums[NA + a] + hp->a_pm[a];
+        if (dbg.normals) {
+            zn[a] = dbg.normals[(size_t)cr * (d_eta + v.p + r) + d_eta + v.p + a];
+        } else {
+            Philox g;
+            g.init(v.seed, gc, (uint32_t)(d_eta + v.p + a), iter, ST_NORMALS);
+            zn[a] = g.normal_d();
+        }
+    }
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.alpha_prec)
+            for (int idx = 0; idx < r * r; idx++) dbg.out.alpha_prec[(size_t)c * r * r + idx] = S[idx];
+        if (dbg.out.alpha_b)
+            for (int a = 0; a < r; a++) dbg.out.alpha_b[(size_t)c * r + a] = b[a];
+    }
+    if (!small_precision_mvnorm(S, r, b, zn, x, tmp)) {
+        v.status[c] = 1;
+        if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+    } else if (!v.status[c]) {
+        for (int a = 0; a < r; a++) v.alpha[(size_t)a * Cp + c] = x[a];
+        if (rec_alpha && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+            const size_t row = (size_t)c * rec_capacity + rec_index;
+            for (int a = 0; a < r; a++) rec_alpha[row * r + a] = x[a];
+        }
+    }
+    Philox g;
+    g.init(v.seed, gc, 0u, iter, ST_TAU);
+    v.gam[c] = gamma_draw(hp->tau_shape, g);
+}
+
+// asum[k][c] = sum_tile apart[tile][k][c], fixed order
+__global__ void reduce_partials_kernel(const View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)v.NV * v.Cp;
+    if (idx >= per) return;
+    double s = 0.0;
+    for (int t = 0; t < v.n_tiles; t++) s += v.apart[(size_t)t * per + idx];
+    v.asum[idx] = s;
+}
+
 // ---- 4x4-blocked Cholesky machinery of the RSR solve ------------------------------------------------
 // Lambda (q x q, padded to qb = ceil(q/4) blocks with an identity tail) plus ONE extra block row holding the
 // right-hand side b (row 0 of block row qb) are kept in shared memory as packed lower-triangular 4x4 blocks,
@@ -684,14 +740,16 @@ constexpr int BLK = 17;
 __device__ __forceinline__ int bidx(int I, int K) { return (I * (I + 1) / 2 + K) * BLK; }
 
 // lower Cholesky of a 4x4 block held in registers (a[r][c], c <= r used); returns false on a bad pivot
-__device__ __forceinline__ bool chol4(double (&a)[4][4]) {
+// (inv[j] = 1 / L_jj; one rsqrt per pivot instead of a sqrt and a divide on the critical path)
+__device__ __forceinline__ bool chol4(double (&a)[4][4], double (&invd)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         double d = a[j][j];
 #pragma unroll
         for (int k = 0; k < j; k++) d -= a[j][k] * a[j][k];
         if (!(d > 0.0)) return false;
-        const double dj = sqrt(d), inv = 1.0 / dj;
+        const double inv = rsqrt(d), dj = d * inv;
+        invd[j] = inv;
         a[j][j] = dj;
 #pragma unroll
         for (int i = j + 1; i < 4; i++) {
@@ -725,7 +783,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     double* red = nrm + q4 + 2 * MAX_SMALL;   // [8]
     double* Ld = red + 8;                     // [qb][16] factored diagonal blocks (kept apart: the panel threads
                                               //          read the unfactored block while its owner factorises it)
-    uint8_t* pair_i = reinterpret_cast<uint8_t*>(Ld + qb * 16);
+    double* Li = Ld + qb * 16;                // [qb][4] reciprocals of the diagonal of L
+    uint8_t* pair_i = reinterpret_cast<uint8_t*>(Li + qb * 4);
     uint8_t* pair_k = pair_i + nblk;
     __shared__ double small_S[MAX_SMALL * MAX_SMALL];
     __shared__ double small_b[MAX_SMALL], small_x[MAX_SMALL], small_t[MAX_SMALL];
@@ -788,14 +847,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
             double quad = 0.0;
             for (int w = 0; w < T / 32; w++) quad += red[w];
             const double rate = 0.5 * quad + hp->tau_rate;
-            double tau;
-            if (dbg.tau_in) {
-                tau = dbg.tau_in[cr];
-            } else {
-                Philox g;
-                g.init(v.seed, gc, 0u, iter, ST_TAU);
-                tau = gamma_draw(hp->tau_shape, g) / rate;
-            }
+            const double tau = dbg.tau_in ? dbg.tau_in[cr] : v.gam[c] / rate;
             red[T / 32] = tau;
             if (dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
         }
@@ -848,16 +900,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
             for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) d[a][b] = dj[a * 4 + b];
-            if (!chol4(d)) {
+            double invd[4];
+            if (!chol4(d, invd)) {
                 ok_flag = 0;
                 continue;
             }
             double* blk = Bs + bidx(I, J);
             if (I == J) {
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 4; a++) {
 #pragma unroll
                     for (int b = 0; b < 4; b++) Ld[J * 16 + a * 4 + b] = b <= a ? d[a][b] : 0.0;
+                    Li[J * 4 + a] = invd[a];
+                }
             } else {  // P = A_IJ L_JJ^-T, row by row
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
@@ -867,7 +922,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
                         double t = blk[a * 4 + b];
 #pragma unroll
                         for (int k = 0; k < b; k++) t -= x[k] * d[b][k];
-                        x[b] = t / d[b][b];
+                        x[b] = t * invd[b];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; b++) blk[a * 4 + b] = x[b];
@@ -933,8 +988,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
                     tm -= L[k * 4 + a] * rm[k];
                     te -= L[k * 4 + a] * re[k];
                 }
-                rm[a] = tm / L[a * 4 + a];
-                re[a] = te / L[a * 4 + a];
+                rm[a] = tm * Li[I * 4 + a];
+                re[a] = te * Li[I * 4 + a];
             }
 #pragma unroll
             for (int a = 0; a < 4; a++) {
@@ -986,26 +1041,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     }
     __syncthreads();
 
-    // ---- alpha | .   A = W_e' Om_a W_e + a_prec,  b = W_e'(y_e - 1/2) + a_prec a_mu   (logit.py:219-224) ----
-    const int NA = r * (r + 1) / 2;
-    for (int idx = tid; idx < r * r; idx += T) {
-        const int a = idx / r, b = idx - a * r;
-        const int k = (b <= a) ? tri(a, b) : tri(b, a);
-        small_S[idx] = v.asum[(size_t)k * Cp + c] + hp->a_prec[idx];
-    }
-    for (int a = tid; a < r; a += T) small_b[a] = v.asum[(size_t)(NA + a) * Cp + c] + hp->a_pm[a];
-    __syncthreads();
-    if (dbg.enabled && c < v.C) {
-        if (dbg.out.alpha_prec)
-            for (int idx = tid; idx < r * r; idx += T) dbg.out.alpha_prec[(size_t)c * r * r + idx] = small_S[idx];
-        if (dbg.out.alpha_b)
-            for (int a = tid; a < r; a += T) dbg.out.alpha_b[(size_t)c * r + a] = small_b[a];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (!small_precision_mvnorm(small_S, r, small_b, nrm + q4 + p, small_x, small_t)) ok_flag = 0;
-    }
-    __syncthreads();
     if (!ok_flag) {
         if (tid == 0) {
             v.status[c] = 1;
@@ -1016,11 +1051,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
 
     // ---- commit state, record the draw (Chain.append, chain.py:56-74) ----
     for (int a = tid; a < pq; a += T) v.theta[(size_t)a * Cp + c] = th[a];
-    for (int a = tid; a < r; a += T) v.alpha[(size_t)a * Cp + c] = small_x[a];
     if (tid == 0) v.tau[c] = tau;
-    if (rec_alpha && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+    if (rec_beta && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
         const size_t row = (size_t)c * rec_capacity + rec_index;
-        for (int a = tid; a < r; a += T) rec_alpha[row * r + a] = small_x[a];
         for (int a = tid; a < p; a += T) rec_beta[row * p + a] = th[a];
         if (tid == 0) rec_tau[row] = tau;
     }
@@ -1292,14 +1325,7 @@ __global__ void __launch_bounds__(ICAR_THREADS) solve_logit_icar_kernel(const Vi
     __syncthreads();
     if (tid == 0) {
         const double rate = 0.5 * quad + hp->tau_rate;
-        double tau;
-        if (dbg.tau_in) {
-            tau = dbg.tau_in[cr];
-        } else {
-            Philox g;
-            g.init(v.seed, gc, 0u, iter, ST_TAU);
-            tau = gamma_draw(hp->tau_shape, g) / rate;
-        }
+        const double tau = dbg.tau_in ? dbg.tau_in[cr] : v.gam[c] / rate;
         red[4] = tau;
         if (dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
     }
@@ -1485,26 +1511,6 @@ __global__ void __launch_bounds__(ICAR_THREADS) solve_logit_icar_kernel(const Vi
     }
     __syncthreads();
 
-    // ---- alpha | . (logit.py:219-224) ----
-    const int NA = r * (r + 1) / 2;
-    for (int idx = tid; idx < r * r; idx += T) {
-        const int a = idx / r, b = idx - a * r;
-        const int k = (b <= a) ? tri(a, b) : tri(b, a);
-        small_S[idx] = v.asum[(size_t)k * Cp + c] + hp->a_prec[idx];
-    }
-    for (int a = tid; a < r; a += T) small_b[a] = v.asum[(size_t)(NA + a) * Cp + c] + hp->a_pm[a];
-    __syncthreads();
-    if (dbg.enabled && c < v.C) {
-        if (dbg.out.alpha_prec)
-            for (int idx = tid; idx < r * r; idx += T) dbg.out.alpha_prec[(size_t)c * r * r + idx] = small_S[idx];
-        if (dbg.out.alpha_b)
-            for (int a = tid; a < r; a += T) dbg.out.alpha_b[(size_t)c * r + a] = small_b[a];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (!small_precision_mvnorm(small_S, r, small_b, nrm + p, small_x, small_t)) ok_flag = 0;
-    }
-    __syncthreads();
     if (!ok_flag) {
         if (tid == 0) {
             v.status[c] = 1;
@@ -1513,11 +1519,9 @@ __global__ void __launch_bounds__(ICAR_THREADS) solve_logit_icar_kernel(const Vi
         return;
     }
     for (int a = tid; a < p; a += T) v.theta[(size_t)a * Cp + c] = beta_s[a];
-    for (int a = tid; a < r; a += T) v.alpha[(size_t)a * Cp + c] = small_x[a];
     if (tid == 0) v.tau[c] = tau;
-    if (rec_alpha && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+    if (rec_beta && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
         const size_t row = (size_t)c * rec_capacity + rec_index;
-        for (int a = tid; a < r; a += T) rec_alpha[row * r + a] = small_x[a];
         for (int a = tid; a < p; a += T) rec_beta[row * p + a] = beta_s[a];
         if (tid == 0) rec_tau[row] = tau;
     }
@@ -1530,8 +1534,14 @@ template <typename PGT>
 static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
+    const size_t smem = (size_t)SITE_TILE * CHAIN_TILE * sizeof(PGT);
     switch (v.r) {
-#define CASE(R) case R: site_pass_logit_kernel<R, PGT><<<grid, CHAIN_TILE, 0, st>>>(v); break;
+#define CASE(R)                                                                                                      \
+    case R:                                                                                                          \
+        if (smem > 48 * 1024)                                                                                        \
+            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        site_pass_logit_kernel<R, PGT><<<grid, CHAIN_TILE, smem, st>>>(v);                                            \
+        break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
@@ -1606,7 +1616,7 @@ static size_t icar_smem_bytes(const View& v) {
 static size_t solve_smem_bytes(const View& v) {
     const size_t qb = (v.q + 3) / 4, q4 = qb * 4;
     const size_t nblk = (qb + 1) * (qb + 2) / 2;
-    const size_t doubles = nblk * 17 + q4 * v.p + (size_t)v.p * v.p + 2 * (size_t)v.pq + 4 + 3 * q4 + 2 * MAX_SMALL + 8 + qb * 16;
+    const size_t doubles = nblk * 17 + q4 * v.p + (size_t)v.p * v.p + 2 * (size_t)v.pq + 4 + 3 * q4 + 2 * MAX_SMALL + 8 + qb * 20;
     return doubles * sizeof(double) + 2 * nblk + 16;
 }
 
@@ -1636,7 +1646,8 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     PROF_MARK(e, KC_REDUCE, st);
     const size_t per = (size_t)v.NV * v.Cp;
     reduce_partials_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(v);
-    e->launches++;
+    alpha_tau_kernel<<<(v.Cp + 31) / 32, 32, 0, st>>>(v, dbg, ra, cap);  // 1 warp per CTA: spread over all SMs
+    e->launches += 2;
     PROF_MARK(e, KC_SOLVE, st);
     if (v.model == OCCU_LOGIT_ICAR) {
         const size_t smem_i = icar_smem_bytes(v);
