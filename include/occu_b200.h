@@ -133,6 +133,16 @@ int occu_reset(occu_engine_t* eng, void* stream);
 int occu_sweep(occu_engine_t* eng, int n_iters, double* rec_alpha, double* rec_beta, double* rec_tau,
                int rec_start, int rec_capacity, void* stream);
 
+/*
+ * The two halves of occu_sweep: occu_sweep_enqueue only enqueues the kernels of `n_iters` iterations on `stream`
+ * (no host synchronisation), occu_finish synchronises the stream and returns the number of failed chains.  Two
+ * engines holding disjoint chain blocks of the same problem can be enqueued on two streams of one GPU so that one
+ * block's sampling kernels (integer / FP32 pipes) overlap the other block's Gram GEMM (FP64 tensor pipe).
+ */
+int occu_sweep_enqueue(occu_engine_t* eng, int n_iters, double* rec_alpha, double* rec_beta, double* rec_tau,
+                       int rec_start, int rec_capacity, void* stream);
+int occu_finish(occu_engine_t* eng, void* stream);
+
 /* Number of kernels launched by this engine so far (bench.py's gpu_launches). */
 long long occu_launch_count(const occu_engine_t* eng);
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liboccu_b200.so')
+LIB_PATH = os.environ.get('OCCU_B200_LIB') or os.path.join(_HERE, 'liboccu_b200.so')
 
 ABI_VERSION = 1
 LOGIT_RSR, PROBIT_RSR, LOGIT_ICAR = 0, 1, 2
@@ -47,6 +47,8 @@ SIGNATURES = {
     'occu_get_field': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_reset': (C.c_int, [C.c_void_p, C.c_void_p]),
     'occu_sweep': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'occu_sweep_enqueue': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'occu_finish': (C.c_int, [C.c_void_p, C.c_void_p]),
     'occu_launch_count': (C.c_longlong, [C.c_void_p]),
     'occu_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'occu_get_kernel_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),

@@ -153,6 +153,23 @@ class DeviceEngine:
             return _lib.check(self.lib.occu_sweep(self.handle, int(n_iters), ra, rb, rt, int(rec_start), int(cap),
                                                   self.stream.cuda_stream), 'occu_sweep')
 
+    def sweep_enqueue(self, n_iters, record=None, rec_start=0):
+        """Enqueue ``n_iters`` iterations on this engine's stream without waiting (pair with ``finish``)."""
+        if record is None:
+            ra = rb = rt = None
+            cap = 0
+        else:
+            ra, rb, rt = record['alpha'].data_ptr(), record['beta'].data_ptr(), record['tau'].data_ptr()
+            cap = record['tau'].shape[1]
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.occu_sweep_enqueue(self.handle, int(n_iters), ra, rb, rt, int(rec_start), int(cap),
+                                                   self.stream.cuda_stream), 'occu_sweep_enqueue')
+
+    def finish(self):
+        """Wait for everything enqueued on this engine; returns the number of failed chains."""
+        with self.torch.cuda.device(self.device):
+            return _lib.check(self.lib.occu_finish(self.handle, self.stream.cuda_stream), 'occu_finish')
+
     @property
     def launches(self):
         return int(self.lib.occu_launch_count(self.handle))
