@@ -69,7 +69,7 @@ typedef struct {
     int32_t chains;       /* chains advanced in lock-step on this device */
     int32_t chain_offset; /* global id of this device's first chain (Philox stream id) */
     int32_t debug;        /* 1: keep occupancy probabilities / allow occu_debug_* */
-    int32_t pg_fp64;      /* 1: PG sampler transcendental work in FP64 (validation), 0: FP32 */
+    int32_t pg_fp64;      /* 1: PG / truncated-normal sampler transcendental work in FP64 (validation), 0: FP32 */
     int32_t icar_bw;      /* ICAR: half bandwidth of Q in the given site order; else 0 */
     uint64_t seed;        /* Philox key (random_state of the sampler) */
     const double* X;      /* [n][p] */
@@ -188,9 +188,10 @@ int occu_debug_site_half(occu_engine_t* eng, int keep_z, const double* u_site, c
 int occu_pg1(const double* c, size_t count, uint64_t seed, int fp64, double* out, void* stream);
 
 /* out[i] ~ N(loc[i], 1) truncated to (0, inf) if positive[i] else (-inf, 0).  `u` (may be NULL) injects the
- * uniforms of the reference's inverse-CDF formula.  Replaces truncnorm_inf_ppf / truncnorm_neginf_ppf
+ * uniforms of the reference's inverse-CDF formula (always FP64); otherwise Philox draws with the transcendental
+ * work in FP64 (fp64 != 0, validation) or FP32 (production).  Replaces truncnorm_inf_ppf / truncnorm_neginf_ppf
  * (probit.py:11-24). */
-int occu_truncnorm(const double* loc, const uint8_t* positive, const double* u, size_t count, uint64_t seed,
+int occu_truncnorm(const double* loc, const uint8_t* positive, const double* u, size_t count, uint64_t seed, int fp64,
                    double* out, void* stream);
 
 /* out[i] ~ Gamma(shape[i], scale = 1 / rate[i])  (rng.gamma at logit.py:209 / probit.py:214). */

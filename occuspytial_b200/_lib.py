@@ -56,7 +56,8 @@ SIGNATURES = {
                                            C.c_void_p]),
     'occu_debug_site_half': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'occu_pg1': (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
-    'occu_truncnorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p]),
+    'occu_truncnorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p,
+                                 C.c_void_p]),
     'occu_gamma': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p]),
     'occu_precision_mvnorm_batched': (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                 C.c_void_p, C.c_void_p]),

@@ -508,7 +508,7 @@ struct SiteDebug {
 // site pass (probit): z | ., omega_a (truncated normal) + alpha partial sums, omega_b, eps, d = omega_b - eps
 // No rejection loops (inverse-CDF draws), so the lanes stay in lock-step over the sites of the tile.
 // ------------------------------------------------------------------------------------------------
-template <int R>
+template <int R, bool F64>
 __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View
                 } else {
                     Philox g;
                     g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
-                    oma = truncnorm_draw(lin, positive, g);
+                    oma = F64 ? truncnorm_draw(lin, positive, g) : truncnorm_draw_f32(lin, positive, g);
                 }
                 int idx = 0;
 #pragma unroll
@@ -594,8 +594,8 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View
         g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
         const double loc = lp + ep;
         const double omb = dbg.u_site ? truncnorm_icdf(loc, zc == 1, dbg.u_site[(size_t)cr * v.n + i])
-                                      : truncnorm_draw(loc, zc == 1, g);
-        const double nz = dbg.nrm_eps ? dbg.nrm_eps[(size_t)cr * v.n + i] : g.normal_d();
+                                      : (F64 ? truncnorm_draw(loc, zc == 1, g) : truncnorm_draw_f32(loc, zc == 1, g));
+        const double nz = dbg.nrm_eps ? dbg.nrm_eps[(size_t)cr * v.n + i] : (F64 ? g.normal_d() : normal_f32(g));
         const double ep_new = 0.5 * (omb - lp) + nz * 0.70710678118654752440;
         v.omega[off] = omb;
         v.eps[off] = ep_new;
@@ -1082,7 +1082,8 @@ __global__ void pg1_kernel(const double* __restrict__ c, size_t count, uint64_t 
 }
 
 __global__ void truncnorm_kernel(const double* __restrict__ loc, const uint8_t* __restrict__ positive,
-                                 const double* __restrict__ u, size_t count, uint64_t seed, double* __restrict__ out) {
+                                 const double* __restrict__ u, size_t count, uint64_t seed, int fp64,
+                                 double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     if (u) {
@@ -1090,7 +1091,7 @@ __global__ void truncnorm_kernel(const double* __restrict__ loc, const uint8_t* 
     } else {
         Philox g;
         g.init(seed, (uint32_t)(i >> 32), (uint32_t)i, 0u, ST_HOOK);
-        out[i] = truncnorm_draw(loc[i], positive[i] != 0, g);
+        out[i] = fp64 ? truncnorm_draw(loc[i], positive[i] != 0, g) : truncnorm_draw_f32(loc[i], positive[i] != 0, g);
     }
 }
 
@@ -2097,7 +2098,11 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
     if (v.model == OCCU_PROBIT_RSR) {
         dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
         switch (v.r) {
-#define CASE(R) case R: site_pass_probit_kernel<R><<<grid, CHAIN_TILE, 0, st>>>(v, dbg); break;
+#define CASE(R)                                                                             \
+    case R:                                                                                 \
+        if (e->pg_fp64) site_pass_probit_kernel<R, true><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);  \
+        else site_pass_probit_kernel<R, false><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);            \
+        break;
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
         }
@@ -2524,11 +2529,12 @@ int occu_pg1(const double* c, size_t count, uint64_t seed, int fp64, double* out
     return 0;
 }
 
-int occu_truncnorm(const double* loc, const uint8_t* positive, const double* u, size_t count, uint64_t seed, double* out,
-                   void* stream) {
+int occu_truncnorm(const double* loc, const uint8_t* positive, const double* u, size_t count, uint64_t seed, int fp64,
+                   double* out, void* stream) {
     if (!loc || !positive || !out) return set_err("null argument");
     if (!count) return 0;
-    truncnorm_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(loc, positive, u, count, seed, out);
+    truncnorm_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(loc, positive, u, count, seed,
+                                                                                         fp64, out);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -134,6 +134,36 @@ __device__ __forceinline__ double truncnorm_draw(double loc, bool positive, Phil
     return positive ? loc + x : loc - x;
 }
 
+// Production-precision variant: the same draw with the transcendental work in FP32 (one 32-bit uniform for the
+// inverse-CDF branch).  Like the PG draws these are latent random variates, not deterministic quantities; the
+// KS tests against scipy.stats.truncnorm arbitrate (tests/test_gpu_primitives.py).
+__device__ __forceinline__ double truncnorm_draw_f32(double loc, bool positive, Philox& g) {
+    const float a = positive ? -(float)loc : (float)loc;
+    float x;
+    if (a < 5.0f) {
+        const float u = ((float)(g.next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float pa = normcdff(-a);
+        x = -normcdfinvf(pa * u);   // u and 1 - u are exchangeable
+        x = fmaxf(x, a);
+    } else {
+        const float lam = 0.5f * (a + sqrtf(a * a + 4.0f));
+        for (;;) {
+            x = a - __logf(g.unif_f()) / lam;
+            const float d = x - lam;
+            if (g.unif_f() <= __expf(-0.5f * d * d)) break;
+        }
+    }
+    const double xd = (double)x;
+    return positive ? loc + xd : loc - xd;
+}
+
+// N(0,1) in FP32 (Box-Muller, 32-bit uniform for the radius: tail to 6.6 sigma)
+__device__ __forceinline__ double normal_f32(Philox& g) {
+    const float u1 = ((float)g.next_u32() + 0.5f) * (1.0f / 4294967296.0f);
+    const float u2 = g.unif_f();
+    return (double)(sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
+}
+
 // Gamma(shape, 1): Marsaglia & Tsang (2000); shape < 1 through the U^(1/shape) boost.
 __device__ __forceinline__ double gamma_draw(double shape, Philox& g) {
     double boost = 1.0;

@@ -67,19 +67,20 @@ def test_truncnorm_matches_reference_formula_and_scipy(env):
     t = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
     out = torch.empty(N, dtype=torch.float64, device='cuda')
     tl, tp, tu = t(loc), t(pos, np.uint8), t(u)
-    _lib.check(lib.occu_truncnorm(tl.data_ptr(), tp.data_ptr(), tu.data_ptr(), N, 0, out.data_ptr(), None), 'tn')
+    _lib.check(lib.occu_truncnorm(tl.data_ptr(), tp.data_ptr(), tu.data_ptr(), N, 0, 1, out.data_ptr(), None), 'tn')
     got = out.cpu().numpy()
     ref = S.truncnorm_draw(loc, pos, u)   # probit.py:11-24 formula
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
     # Philox path: KS against scipy.stats.truncnorm, including far tails where the reference formula breaks
-    for L, positive in ((0.5, True), (-1.5, True), (2.0, False), (-9.0, True), (12.0, False)):
-        loc1 = np.full(N, L)
-        tl, tp = t(loc1), t(np.full(N, positive), np.uint8)
-        _lib.check(lib.occu_truncnorm(tl.data_ptr(), tp.data_ptr(), None, N, 5, out.data_ptr(), None), 'tn')
-        x = out.cpu().numpy()
-        assert np.all(x > 0) if positive else np.all(x < 0)
-        a, b = ((0 - L), np.inf) if positive else (-np.inf, (0 - L))
-        assert stats.kstest(x, stats.truncnorm(a, b, loc=L).cdf).pvalue > 1e-3
+    for fp64 in (1, 0):
+        for L, positive in ((0.5, True), (-1.5, True), (2.0, False), (-4.5, True), (-9.0, True), (12.0, False)):
+            loc1 = np.full(N, L)
+            tl, tp = t(loc1), t(np.full(N, positive), np.uint8)
+            _lib.check(lib.occu_truncnorm(tl.data_ptr(), tp.data_ptr(), None, N, 5, fp64, out.data_ptr(), None), 'tn')
+            x = out.cpu().numpy()
+            assert np.all(x >= 0) if positive else np.all(x <= 0)
+            a, b = ((0 - L), np.inf) if positive else (-np.inf, (0 - L))
+            assert stats.kstest(x, stats.truncnorm(a, b, loc=L).cdf).pvalue > 1e-3, (fp64, L)
 
 
 def test_gamma(env):
