@@ -1,0 +1,68 @@
+"""Full-size checks (BASELINE.json metric configuration: LogitRSRGibbs, n = 10 000 sites, q = 64, 4096 chains)
+through size-independent properties: the oracle cannot run this size in seconds, invariants can."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def big():
+    from occuspytial_b200 import LogitRSRGibbs
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.gibbs import _setup
+    Q, W, X, y, alpha, beta, tau, z = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random_state=0)
+    K = _setup.rsr_basis(Q, X, q=64)
+    return LogitRSRGibbs(Q, W, X, y, random_state=10, K=K), alpha
+
+
+def test_full_size_invariants(big):
+    from occuspytial_b200 import _lib
+    from oracle import sweep as S
+    s, alpha_true = big
+    C = 4096
+    eng = s._make_engine(C, seed=99)
+    start = s._start_arrays(C, None)
+    eng.set_start(start)
+    rec = eng.alloc_record(25)
+    assert eng.sweep(25, rec, 0) == 0                       # no chain lost positive-definiteness
+    draws = {k: v.cpu().numpy() for k, v in rec.items()}
+    assert all(np.all(np.isfinite(v)) for v in draws.values()) and np.all(draws['tau'] > 0)
+    # state invariants
+    z = eng.get_field(_lib.F_Z)
+    assert set(np.unique(z)) <= {0, 1}
+    cls = s.fixed.site_class
+    assert np.all(z[:, cls == 2] == 1)                      # detection implies occupancy (base.py:118)
+    assert 0 < z[:, cls == 1].mean() < 1 and 0 < z[:, cls == 0].mean() < 1
+    # psi = X beta + K eta on every chain, to rounding (the DMMA GEMM at full size)
+    beta, eta = eng.get_field(_lib.F_BETA), eng.get_field(_lib.F_ETA)
+    eng.sweep(1)                                            # psi of the state just read is computed first ...
+    psi = eng.get_field(_lib.F_PSI)
+    ref = beta @ s.X.T + eta @ s.fixed.K.T
+    np.testing.assert_allclose(psi, ref, rtol=1e-11, atol=1e-11)
+    # ... and omega_b ~ PG(1, psi): law of large numbers over 4 x 10^7 draws against the analytic mean / variance
+    omega = eng.get_field(_lib.F_OMEGA)
+    assert np.all(omega > 0) and np.all(np.isfinite(omega))
+    resid = (omega - S.pg1_mean(psi)) / np.sqrt(S.pg1_var(psi))
+    assert abs(resid.mean()) < 1e-3 and abs(resid.var() - 1) < 5e-3
+    # the chains have moved towards the data-generating alpha (loose sanity, 26 iterations from diffuse starts)
+    assert np.linalg.norm(np.median(draws['alpha'][:, -1], axis=0) - alpha_true) < 0.5
+    eng.close()
+
+
+def test_full_size_sharding_and_determinism(big):
+    """Chains 128..255 of a 256-chain job are bit-identical to a 128-chain engine at offset 128 (what a second
+    GPU would run), and a rerun reproduces the draws bit for bit."""
+    s, _ = big
+    start = s._start_arrays(256, None)
+    out = []
+    for chains, off in ((256, 0), (128, 128), (256, 0)):
+        eng = s._make_engine(chains, seed=5, chain_offset=off)
+        eng.set_start({k: v[off:off + chains] for k, v in start.items()})
+        rec = eng.alloc_record(4)
+        eng.sweep(4, rec, 0)
+        out.append({k: v.cpu().numpy() for k, v in rec.items()})
+        eng.close()
+    for k in ('alpha', 'beta', 'tau'):
+        np.testing.assert_array_equal(out[0][k][128:], out[1][k])
+        np.testing.assert_array_equal(out[0][k], out[2][k])
