@@ -95,6 +95,8 @@ struct View {
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
     double* gam;    // [Cp]  Gamma(tau_shape, 1) variates of this iteration
+    double* solve_scratch;  // [Cp][solve_stride] working set of the RSR solve when it exceeds shared memory, else NULL
+    size_t solve_stride;    // doubles per chain (0: shared-memory path)
     double* zprob;  // [n][Cp] or NULL
     double* eps;    // [n_pad][Cp]  probit only
     // ICAR only
@@ -139,6 +141,15 @@ struct Carver {
     }
 };
 
+// bytes of the RSR solve kernel's working set (shared memory, or per-chain global scratch for large q);
+// must mirror the carve at the top of solve_logit_rsr_kernel
+static size_t solve_bytes_for(int q, int p, int pq) {
+    const size_t qb = (q + 3) / 4, q4 = qb * 4;
+    const size_t nblk = (qb + 1) * (qb + 2) / 2;
+    const size_t doubles = nblk * 17 + q4 * p + (size_t)p * p + 2 * (size_t)pq + 4 + 3 * q4 + 2 * MAX_SMALL + 8 + qb * 20;
+    return doubles * sizeof(double) + 2 * nblk + 16;
+}
+
 static int fill_dims(const occu_problem_t* P, View& v) {
     if (!P) return set_err("null problem");
     if (P->abi_version != OCCU_ABI_VERSION) return set_err("ABI version mismatch");
@@ -179,9 +190,11 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     // solve kernel keeps Lambda (4x4-blocked, packed lower triangle) and a few vectors in shared memory
     if (!icar) {
         const size_t qb = (v.q + 3) / 4;
-        const size_t solve_smem = ((qb + 1) * (qb + 2) / 2 * 17 + 4 * qb * (v.p + 3) + (size_t)v.p * v.p + 2 * v.pq + 128) * 8;
-        if (solve_smem > 200 * 1024) return set_err("RSR rank q too large for the shared-memory solve (q <= ~200)");
-        if (qb > 254) return set_err("RSR rank q too large");
+        const size_t solve_smem = solve_bytes_for(v.q, v.p, v.pq);
+        // beyond ~200 the blocked factor no longer fits in shared memory: the same kernel then works out of a
+        // per-chain global scratch block (L1/L2-cached; functional large-q path, SURVEY 8(f) row 4 is the fast one)
+        v.solve_stride = solve_smem > 200 * 1024 ? (solve_smem + 64) / 8 : 0;
+        if (qb > SOLVE_THREADS) return set_err("RSR rank q too large (q <= 512 in this build)");
     }
     return 0;
 }
@@ -219,6 +232,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.apart = c.take<double>((size_t)v.n_tiles * v.NV * Cp);
     v.asum = c.take<double>((size_t)v.NV * Cp);
     v.gam = c.take<double>(Cp);
+    v.solve_scratch = v.solve_stride ? c.take<double>(Cp * v.solve_stride) : nullptr;
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
     v.status = c.take<int32_t>(Cp);
     *total = align_up(c.off, 256);
@@ -775,8 +789,9 @@ __device__ __forceinline__ bool chol4(double (&a)[4][4], double (&invd)[4]) {
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
                                                                          double* rec_alpha, double* rec_beta,
                                                                          double* rec_tau, int rec_capacity) {
-    extern __shared__ double sm[];
+    extern __shared__ double sm_dyn[];
     const int c = blockIdx.x, tid = threadIdx.x, T = SOLVE_THREADS;
+    double* sm = v.solve_stride ? v.solve_scratch + (size_t)c * v.solve_stride : sm_dyn;
     const int p = v.p, q = v.q, r = v.r, pq = v.pq;
     const int qb = (q + 3) / 4, q4 = qb * 4;
     const int nblk = (qb + 1) * (qb + 2) / 2;  // lower-triangular blocks incl. the right-hand-side block row
@@ -2162,12 +2177,7 @@ static size_t icar_smem_bytes(const View& v) {
     return (W1 * W1 + 6 * W1 + 2 * MAX_SMALL + 8) * sizeof(double) + (size_t)v.bw * (v.bw + 1) + 16;
 }
 
-static size_t solve_smem_bytes(const View& v) {
-    const size_t qb = (v.q + 3) / 4, q4 = qb * 4;
-    const size_t nblk = (qb + 1) * (qb + 2) / 2;
-    const size_t doubles = nblk * 17 + q4 * v.p + (size_t)v.p * v.p + 2 * (size_t)v.pq + 4 + 3 * q4 + 2 * MAX_SMALL + 8 + qb * 20;
-    return doubles * sizeof(double) + 2 * nblk + 16;
-}
+static size_t solve_smem_bytes(const View& v) { return solve_bytes_for(v.q, v.p, v.pq); }
 
 #define PROF_MARK(e, k, st)                                           \
     do {                                                              \
@@ -2217,7 +2227,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    const size_t smem = solve_smem_bytes(v);
+    const size_t smem = v.solve_stride ? 0 : solve_smem_bytes(v);
     static size_t configured = 0;
     if (smem > configured) {
         CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -80,7 +80,7 @@ def test_beta_draw_vs_reference_golden_via_huge_precision():
     eng.close()
 
 
-@pytest.mark.parametrize('q,chains', [(7, 5), (64, 130)])
+@pytest.mark.parametrize('q,chains', [(7, 5), (64, 130), (230, 3)])   # q = 230: the solve works out of global scratch
 def test_full_iteration_pieces_vs_oracle(q, chains):
     """Random states, several chains (incl. a padded tail and > 1 chain tile): every system of the Gaussian
     half and the z probabilities agree with the oracle to 1e-10."""
