@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--pg-fp64', action='store_true')
+    ap.add_argument('--gram', default='dmma', choices=['dmma', 'int8'],
+                    help='Omega-weighted Gram: hand-written FP64 DMMA kernel (default) or exact INT8 slice GEMMs')
     return ap.parse_args()
 
 
@@ -196,7 +198,7 @@ def run_b200(args):
     seed = 12345
     start = sampler._start_arrays(chains_total, None)
     start = {k: v[lo:lo + args.chains] for k, v in start.items()}
-    eng = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64)
+    eng = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=args.gram == 'int8')
     eng.set_start(start)
     rec = eng.alloc_record(args.steps)
     fails = eng.sweep(args.warmup)
@@ -249,7 +251,7 @@ def run_b200(args):
             dist.barrier()
         t0 = time.perf_counter()
         post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, chains=chains_total, progressbar=False,
-                              pg_fp64=args.pg_fp64)
+                              pg_fp64=args.pg_fp64, gram_int8=args.gram == 'int8')
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         st = sampler._last_stats

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('OCCU_B200_LIB') or os.path.join(_HERE, 'liboccu_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LOGIT_RSR, PROBIT_RSR, LOGIT_ICAR = 0, 1, 2
 SITE_NOT_SURVEYED, SITE_NOT_OBS, SITE_OBS = 0, 1, 2
 F_ALPHA, F_BETA, F_ETA, F_TAU, F_Z, F_OMEGA, F_PSI, F_EPS, F_ZPROB = range(9)
@@ -22,7 +22,7 @@ class Problem(C.Structure):
         ('abi_version', C.c_int32), ('model', C.c_int32), ('n', C.c_int32), ('p', C.c_int32),
         ('r', C.c_int32), ('q', C.c_int32), ('V', C.c_int32), ('chains', C.c_int32),
         ('chain_offset', C.c_int32), ('debug', C.c_int32), ('pg_fp64', C.c_int32), ('icar_bw', C.c_int32),
-        ('seed', C.c_uint64),
+        ('gram_int8', C.c_int32), ('seed', C.c_uint64),
         ('X', C.c_void_p), ('K', C.c_void_p), ('Qrsr', C.c_void_p), ('Qband', C.c_void_p),
         ('W', C.c_void_p), ('y', C.c_void_p), ('visit_ptr', C.c_void_p), ('site_class', C.c_void_p),
         ('tau_rate', C.c_double), ('tau_shape', C.c_double),

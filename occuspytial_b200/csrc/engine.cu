@@ -24,6 +24,7 @@
 #include "../../include/occu_b200.h"
 #include "common.cuh"
 #include "gemm_dmma.cuh"
+#include "gram_int8.cuh"
 #include "samplers.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -56,6 +57,7 @@ constexpr int SITE_TILE = SITE_TILE_N;
 constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
 constexpr int SOLVE_THREADS = 128;
 constexpr int MAX_SMALL = 32;    // max p and r
+constexpr size_t LT_WS_BYTES = 64u << 20;  // cuBLASLt workspace of the INT8 Gram path
 
 struct Control {
     uint32_t iter;     // iteration counter (Philox coordinate)
@@ -95,6 +97,17 @@ struct View {
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
     double* gam;    // [Cp]  Gamma(tau_shape, 1) variates of this iteration
+    // optional exact-integer Gram path (gram_int8.cuh)
+    int int8;               // 1: G and H come from INT8 slice GEMMs
+    int n_jobs;
+    int8_t* Aq;             // [Cp][SA][n_pad]   base-128 digits of omega / 8
+    int8_t* k2q;            // [Cp][n_pad]       2 (z - 1/2)
+    int8_t* Bq;             // [ldz][SB][n_pad]  balanced base-128 digits of [Z | U] / column scale, reversed slice order
+    double* bscale;         // [ldz]
+    int32_t* Cbuf;          // [n_jobs][Cp][M_pad]
+    int32_t* Hbuf;          // [Cp][ldh * SB]
+    int* job_levels;        // [MAX_JOBS]
+    void* lt_ws;            // cuBLASLt workspace
     double* solve_scratch;  // [Cp][solve_stride] working set of the RSR solve when it exceeds shared memory, else NULL
     size_t solve_stride;    // doubles per chain (0: shared-memory path)
     double* zprob;  // [n][Cp] or NULL
@@ -120,6 +133,9 @@ struct occu_engine {
     long long launches;
     char* ws;
     size_t ws_bytes;
+    cublasLtHandle_t lt;
+    gint8::Plan plan;
+    gint8::LtGemm job_gemm[gint8::MAX_JOBS], h_gemm;
     int profiling;
     double kernel_ms[KC_COUNT];
     long long kernel_calls[KC_COUNT];
@@ -178,6 +194,11 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     v.ldh = round_up(v.pq, dgemm::BN);
     v.ldz = v.M_pad + v.ldh;
     v.ksplit = (v.n_pad / dgemm::BK >= 64) ? 8 : 1;
+    v.int8 = (P->gram_int8 && P->model == OCCU_LOGIT_RSR) ? 1 : 0;
+    if (v.int8) {
+        v.ksplit = 1;
+        v.n_jobs = gint8::make_plan(v.n_pad).njobs;
+    }
     if (P->model == OCCU_PROBIT_RSR) {
         // only the K-split product U'd runs: split it until the grid covers the GPU (2 CTAs x 148 SMs)
         const int tiles = (v.Cp / dgemm::BM) * (v.ldh / dgemm::BN);
@@ -233,6 +254,16 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.asum = c.take<double>((size_t)v.NV * Cp);
     v.gam = c.take<double>(Cp);
     v.solve_scratch = v.solve_stride ? c.take<double>(Cp * v.solve_stride) : nullptr;
+    if (v.int8) {
+        v.Aq = c.take<int8_t>(Cp * (size_t)gint8::SA * v.n_pad);
+        v.k2q = c.take<int8_t>(Cp * (size_t)v.n_pad);
+        v.Bq = c.take<int8_t>((size_t)v.ldz * gint8::SB * v.n_pad);
+        v.bscale = c.take<double>(v.ldz);
+        v.Cbuf = c.take<int32_t>((size_t)v.n_jobs * Cp * v.M_pad);
+        v.Hbuf = c.take<int32_t>(Cp * (size_t)v.ldh * gint8::SB);
+        v.job_levels = c.take<int>(gint8::MAX_JOBS);
+        v.lt_ws = c.take<char>(LT_WS_BYTES);
+    }
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
     v.status = c.take<int32_t>(Cp);
     *total = align_up(c.off, 256);
@@ -2159,8 +2190,38 @@ static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
     return 0;
 }
 
+// G and H through INT8 slice GEMMs (gram_int8.cuh)
+static int launch_gram_int8(occu_engine* e, cudaStream_t st) {
+    const View& v = e->v;
+    gint8::slice_a_kernel<<<dim3(v.n_pad / 32, v.Cp / 32), 256, 0, st>>>(v.omega, v.kd, v.n, v.n_pad, v.Cp, v.Aq, v.k2q);
+    e->launches++;
+    const size_t job_stride = (size_t)v.Cp * v.M_pad;
+    for (int j = 0; j < e->plan.njobs; j++) {
+        const gint8::Job& jb = e->plan.jobs[j];
+        const int r0 = gint8::SB + 1 - jb.level + jb.s0;  // reversed slot of the first Z slice of this job (1-based)
+        const int8_t* X = v.Bq + (size_t)(r0 - 1) * v.n_pad;
+        const int8_t* Y = v.Aq + (size_t)(jb.s0 - 1) * v.n_pad;
+        if (gint8::lt_run(e->lt, e->job_gemm[j], X, Y, v.Cbuf + j * job_stride, v.lt_ws, LT_WS_BYTES, st) !=
+            CUBLAS_STATUS_SUCCESS)
+            return set_err("cublasLtMatmul (INT8 Gram) failed");
+        e->launches++;
+    }
+    const int8_t* XU = v.Bq + (size_t)v.M_pad * gint8::SB * v.n_pad;
+    if (gint8::lt_run(e->lt, e->h_gemm, XU, v.k2q, v.Hbuf, v.lt_ws, LT_WS_BYTES, st) != CUBLAS_STATUS_SUCCESS)
+        return set_err("cublasLtMatmul (INT8 H) failed");
+    const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
+    gint8::combine_g_kernel<<<(unsigned)((tg + 255) / 256), 256, 0, st>>>(v.Cbuf, e->plan.njobs, v.job_levels, job_stride,
+                                                                          v.bscale, v.Cp, v.M_pad, v.G);
+    gint8::combine_h_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(v.Hbuf, v.bscale + v.M_pad, v.Cp, v.pq, v.ldh,
+                                                                          v.Hpart);
+    e->launches += 3;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
+    if (v.int8) return launch_gram_int8(e, st);
     dgemm::Args a;
     memset(&a, 0, sizeof(a));
     a.A1 = v.omega; a.B = v.ZU; a.Out = v.G;
@@ -2332,6 +2393,34 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         gram_unit_kernel<<<(v.M + 127) / 128, 128, 0, st>>>(v);
         e->launches++;
     }
+    e->lt = nullptr;
+    if (v.int8) {
+        // slice [Z | U] once; plan the slice-pair GEMMs and let cuBLASLt pick an IMMA algorithm for each shape
+        gint8::column_scale_kernel<<<(v.ldz + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.ldz, v.bscale);
+        gint8::slice_b_kernel<<<dim3((v.n_pad + 255) / 256, v.ldz), 256, 0, st>>>(v.ZU, v.n, v.n_pad, v.ldz, v.ldz, v.bscale,
+                                                                                   v.Bq);
+        e->launches += 2;
+        e->plan = gint8::make_plan(v.n_pad);
+        int levels[gint8::MAX_JOBS] = {0};
+        for (int j = 0; j < e->plan.njobs; j++) levels[j] = e->plan.jobs[j].level;
+        FAIL_IF(cudaMemcpyAsync(v.job_levels, levels, sizeof(levels), cudaMemcpyHostToDevice, st));
+        FAIL_IF(cudaStreamSynchronize(st));
+        if (cublasLtCreate(&e->lt) != CUBLAS_STATUS_SUCCESS) {
+            delete e;
+            return set_err("cublasLtCreate failed");
+        }
+        const char* why = nullptr;
+        for (int j = 0; j < e->plan.njobs && !why; j++)
+            why = gint8::lt_setup(e->lt, e->job_gemm[j], v.M_pad, v.Cp, e->plan.jobs[j].npairs * v.n_pad,
+                                  (size_t)gint8::SB * v.n_pad, (size_t)gint8::SA * v.n_pad, v.M_pad, LT_WS_BYTES);
+        if (!why)
+            why = gint8::lt_setup(e->lt, e->h_gemm, v.ldh * gint8::SB, v.Cp, v.n_pad, v.n_pad, v.n_pad,
+                                  (size_t)v.ldh * gint8::SB, LT_WS_BYTES);
+        if (why) {
+            occu_destroy(e);
+            return set_err("INT8 Gram path: cuBLASLt setup failed (%s)", why);
+        }
+    }
     const size_t total = (size_t)v.n * v.Cp;
     reset_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
     set_control_kernel<<<1, 1, 0, st>>>(v.ctl, 0u, 1, -1, 1);
@@ -2344,6 +2433,11 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
 
 void occu_destroy(occu_engine_t* eng) {
     if (!eng) return;
+    if (eng->lt) {
+        for (int j = 0; j < gint8::MAX_JOBS; j++) gint8::lt_destroy(eng->job_gemm[j]);
+        gint8::lt_destroy(eng->h_gemm);
+        cublasLtDestroy(eng->lt);
+    }
     for (int k = 0; k <= KC_COUNT; k++)
         if (eng->ev[k]) cudaEventDestroy(eng->ev[k]);
     delete eng;

@@ -1,0 +1,196 @@
+// gram_int8.cuh -- optional exact-integer path for the Omega-weighted Gram  G = Omega' Z  (opt-in, gram_int8 = 1).
+//
+// FP64 has no tcgen05 kind; the DMMA path tops out at ~37 TFLOP/s on B200 while the INT8 tensor path is two
+// orders of magnitude wider.  This path evaluates the SAME FP64 contraction by error-free integer slicing
+// (Ozaki-style): with fixed power-of-two scales,
+//     omega / 8      = sum_{s=1..SA} a_s 128^-s,   a_s in [0, 127]      (7 bits per slice, 49 bits)
+//     Z[:, m] / c_m  = sum_{t=1..SB} b_t 128^-t,   b_t in [-64, 64]     (balanced digits, 42 bits, |.| <= 1/2)
+//     G[c][m]        = 8 c_m  sum_{s + t <= LMAX} 128^-(s+t)  sum_i a_s[i][c] b_t[i][m]
+// Every inner sum is an INT8 x INT8 -> INT32 GEMM and therefore EXACT and order-independent; slice pairs of
+// equal weight s + t are concatenated along K into one GEMM (the Z slices are stored in reversed order so that
+// both operand ranges are contiguous), chunked so that no INT32 accumulator can overflow.  The dropped tail
+// (s + t > LMAX) is below 2^-56 of the product scale.  Slicing and recombination are kernels of this file; the
+// integer GEMMs themselves are plain library GEMMs and go to cuBLASLt (IMMA on the tensor cores) -- replacing
+// them by a hand-written tcgen05 kind::i8 kernel is the next step.
+//
+// The default Gram path remains the hand-written FP64 DMMA kernel (gemm_dmma.cuh).
+#pragma once
+#include <cublasLt.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gint8 {
+
+constexpr int SA = 7, SB = 6, LMAX = 8;
+constexpr int MAX_JOBS = 32;
+constexpr double OMEGA_SCALE = 8.0;  // omega / 8 < 1: P(PG(1, c) > 8) < 1e-17 per draw; larger values saturate
+
+struct Job {
+    int level;   // s + t of every pair in this GEMM
+    int s0;      // first omega slice (1-based)
+    int npairs;  // consecutive pairs (s0 + j, level - s0 - j)
+};
+
+struct Plan {
+    int njobs;
+    Job jobs[MAX_JOBS];
+};
+
+inline Plan make_plan(int Kp) {
+    Plan p;
+    p.njobs = 0;
+    // |a_s b_t| <= 127 * 64; keep every INT32 accumulator below 2^31
+    long long maxpairs = (1LL << 31) / (127LL * 64LL * (long long)Kp);
+    if (maxpairs < 1) maxpairs = 1;
+    for (int level = 2; level <= LMAX; level++) {
+        const int s_lo = level - SB > 1 ? level - SB : 1;
+        const int s_hi = level - 1 < SA ? level - 1 : SA;
+        for (int s = s_lo; s <= s_hi && p.njobs < MAX_JOBS;) {
+            int np = s_hi - s + 1;
+            if (np > maxpairs) np = (int)maxpairs;
+            p.jobs[p.njobs++] = Job{level, s, np};
+            s += np;
+        }
+    }
+    return p;
+}
+
+// c_m = 2^(ceil(log2 max_i |Z[i][m]|) + 1)  =>  |Z / c_m| <= 1/2
+__global__ void column_scale_kernel(const double* __restrict__ ZU, int n, int ld, int ncols, double* __restrict__ scale) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ncols) return;
+    double mx = 0.0;
+    for (int i = 0; i < n; i++) mx = fmax(mx, fabs(ZU[(size_t)i * ld + m]));
+    int e = 0;
+    if (mx > 0.0) {
+        frexp(mx, &e);  // mx = f 2^e, f in [0.5, 1)
+        e += 1;
+    }
+    scale[m] = ldexp(1.0, e);
+}
+
+// Bq[m][r][i], r = SB - t (reversed slice order), balanced base-128 digits of Z[i][m] / c_m
+__global__ void slice_b_kernel(const double* __restrict__ ZU, int n, int Kp, int ld, int ncols,
+                               const double* __restrict__ scale, int8_t* __restrict__ Bq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (i >= Kp || m >= ncols) return;
+    double y = i < n ? ZU[(size_t)i * ld + m] / scale[m] : 0.0;
+    int8_t* out = Bq + (size_t)m * SB * Kp + i;
+#pragma unroll
+    for (int t = 1; t <= SB; t++) {
+        y *= 128.0;
+        const double d = rint(y);
+        y -= d;
+        out[(size_t)(SB - t) * Kp] = (int8_t)d;
+    }
+}
+
+// Aq[c][s-1][i]: base-128 digits of omega[i][c] / 8;  k2[c][i] = 2 kd[i][c] (+-1).  32 x 32 tile transpose.
+__global__ void __launch_bounds__(256) slice_a_kernel(const double* __restrict__ omega, const double* __restrict__ kd, int n,
+                                                      int Kp, int Cp, int8_t* __restrict__ Aq, int8_t* __restrict__ k2) {
+    __shared__ int8_t tile[SA + 1][32][36];
+    const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, c = c0 + tx;
+        double x = 0.0, k = 0.0;
+        if (i < n) {
+            x = omega[(size_t)i * Cp + c] * (1.0 / OMEGA_SCALE);
+            k = kd[(size_t)i * Cp + c];
+        }
+        x = fmin(x, 1.0 - 1e-16);
+#pragma unroll
+        for (int s = 0; s < SA; s++) {
+            x *= 128.0;
+            const double d = floor(x);
+            x -= d;
+            tile[s][tx][r] = (int8_t)d;
+        }
+        tile[SA][tx][r] = (int8_t)(2.0 * k);
+    }
+    __syncthreads();
+    // write: for chain c0 + cc, slice s: 32 consecutive bytes
+    for (int idx = threadIdx.x; idx < 32 * (SA + 1) * 8; idx += 256) {
+        const int w4 = idx & 7, rest = idx >> 3;       // 8 words of 4 bytes per (chain, slice) row
+        const int cc = rest & 31, s = rest >> 5;
+        const int c = c0 + cc;
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(&tile[s][cc][w4 * 4]);
+        int8_t* dst = (s < SA) ? Aq + ((size_t)c * SA + s) * Kp : k2 + (size_t)c * Kp;
+        *reinterpret_cast<uint32_t*>(dst + i0 + w4 * 4) = word;
+    }
+}
+
+// G[c][m] = 8 c_m sum_jobs 128^-level C_job[c][m]
+__global__ void combine_g_kernel(const int32_t* __restrict__ Cbuf, int njobs, const int* __restrict__ levels, size_t job_stride,
+                                 const double* __restrict__ scale, int Cp, int M_pad, double* __restrict__ G) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)Cp * M_pad) return;
+    const int m = (int)(idx % M_pad);
+    double acc = 0.0;
+    for (int j = njobs - 1; j >= 0; j--)  // small terms first
+        acc += ldexp((double)Cbuf[(size_t)j * job_stride + idx], -7 * levels[j]);
+    G[idx] = OMEGA_SCALE * scale[m] * acc;
+}
+
+// H[c][a] = 1/2 c_a sum_t 128^-t Hbuf[c][a * SB + (SB - t)]
+__global__ void combine_h_kernel(const int32_t* __restrict__ Hbuf, const double* __restrict__ scale_u, int Cp, int pq, int ldh,
+                                 double* __restrict__ H) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)Cp * ldh) return;
+    const int a = (int)(idx % ldh);
+    const size_t c = idx / ldh;
+    double acc = 0.0;
+    if (a < pq) {
+        const int32_t* row = Hbuf + (c * ldh + a) * SB;
+        for (int t = SB; t >= 1; t--) acc += ldexp((double)row[SB - t], -7 * t);
+        acc *= 0.5 * scale_u[a];
+    }
+    H[idx] = acc;
+}
+
+// One INT8 TN GEMM through cuBLASLt:  C[ncols_c x nrows_c, col-major, ldc] = X' Y, X [k x m] ld ldx, Y [k x n] ld ldy
+struct LtGemm {
+    cublasLtMatmulDesc_t desc = nullptr;
+    cublasLtMatrixLayout_t lx = nullptr, ly = nullptr, lc = nullptr;
+    cublasLtMatmulAlgo_t algo;
+    bool ok = false;
+};
+
+inline const char* lt_setup(cublasLtHandle_t lt, LtGemm& g, int m, int n, int k, size_t ldx, size_t ldy, size_t ldc,
+                            size_t ws_bytes) {
+    if (cublasLtMatmulDescCreate(&g.desc, CUBLAS_COMPUTE_32I, CUDA_R_32I) != CUBLAS_STATUS_SUCCESS) return "desc";
+    const cublasOperation_t opT = CUBLAS_OP_T, opN = CUBLAS_OP_N;
+    cublasLtMatmulDescSetAttribute(g.desc, CUBLASLT_MATMUL_DESC_TRANSA, &opT, sizeof(opT));
+    cublasLtMatmulDescSetAttribute(g.desc, CUBLASLT_MATMUL_DESC_TRANSB, &opN, sizeof(opN));
+    if (cublasLtMatrixLayoutCreate(&g.lx, CUDA_R_8I, k, m, ldx) != CUBLAS_STATUS_SUCCESS) return "layout x";
+    if (cublasLtMatrixLayoutCreate(&g.ly, CUDA_R_8I, k, n, ldy) != CUBLAS_STATUS_SUCCESS) return "layout y";
+    if (cublasLtMatrixLayoutCreate(&g.lc, CUDA_R_32I, m, n, ldc) != CUBLAS_STATUS_SUCCESS) return "layout c";
+    cublasLtMatmulPreference_t pref;
+    if (cublasLtMatmulPreferenceCreate(&pref) != CUBLAS_STATUS_SUCCESS) return "pref";
+    cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes));
+    cublasLtMatmulHeuristicResult_t res;
+    int found = 0;
+    const cublasStatus_t st = cublasLtMatmulAlgoGetHeuristic(lt, g.desc, g.lx, g.ly, g.lc, g.lc, pref, 1, &res, &found);
+    cublasLtMatmulPreferenceDestroy(pref);
+    if (st != CUBLAS_STATUS_SUCCESS || found == 0) return "no INT8 algorithm";
+    g.algo = res.algo;
+    g.ok = true;
+    return nullptr;
+}
+
+inline void lt_destroy(LtGemm& g) {
+    if (g.lx) cublasLtMatrixLayoutDestroy(g.lx);
+    if (g.ly) cublasLtMatrixLayoutDestroy(g.ly);
+    if (g.lc) cublasLtMatrixLayoutDestroy(g.lc);
+    if (g.desc) cublasLtMatmulDescDestroy(g.desc);
+    g = LtGemm();
+}
+
+inline cublasStatus_t lt_run(cublasLtHandle_t lt, const LtGemm& g, const int8_t* X, const int8_t* Y, int32_t* C, void* ws,
+                             size_t ws_bytes, cudaStream_t st) {
+    const int32_t one = 1, zero = 0;
+    return cublasLtMatmul(lt, g.desc, &one, X, g.lx, Y, g.ly, &zero, C, g.lc, C, g.lc, &g.algo, ws, ws_bytes, st);
+}
+
+}  // namespace gint8

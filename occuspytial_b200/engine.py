@@ -34,7 +34,8 @@ class DeviceEngine:
         Number of chains on this device, global id of the first one, Philox key.
     """
 
-    def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False):
+    def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False,
+                 gram_int8=False):
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
@@ -67,6 +68,7 @@ class DeviceEngine:
             P.n, P.p, P.r, P.q, P.V = self.n, self.p, self.r, self.q, self.V
             P.chains, P.chain_offset = self.chains, int(chain_offset)
             P.debug, P.pg_fp64 = int(bool(debug)), int(bool(pg_fp64))
+            P.gram_int8 = int(bool(gram_int8))
             P.icar_bw = int(problem.get('icar_bw', 0))
             P.seed = int(seed) & (2**64 - 1)
             P.X = up('X', X, np.float64)

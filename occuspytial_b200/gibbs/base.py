@@ -179,12 +179,12 @@ class GibbsBase:
                     site_class=f.site_class, tau_rate=f.tau_rate, tau_shape=f.tau_shape,
                     a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
 
-    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False):
+    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=False):
         from ..engine import DeviceEngine
         if self._model is None:
             raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
         return DeviceEngine(self._model, self._problem_arrays(), chains, seed, chain_offset=chain_offset,
-                            device=device, debug=debug, pg_fp64=pg_fp64)
+                            device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8)
 
     def step(self):
         """Step through one iteration of the sampler.
@@ -214,7 +214,7 @@ class GibbsBase:
             self.state.k = self.state.z - 0.5
 
     def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None,
-                      pg_fp64=False):
+                      pg_fp64=False, gram_int8=False):
         """All chains of this process in lock-step on one device; returns the list of ``Chain`` views.
 
         Under torch.distributed the global ``chains`` are sharded contiguously over ranks and only the
@@ -236,7 +236,7 @@ class GibbsBase:
         if local <= 0:
             return []
         arrays = {k: v[lo:hi] for k, v in arrays.items()}
-        engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64)
+        engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8)
         try:
             engine.set_start(self._start_to_engine(arrays))
             draws = size - burnin
@@ -308,7 +308,8 @@ class GibbsBase:
         progressbar : bool, optional
             Whether to display the progress bar during sampling.
         **engine_kwargs
-            Engine knobs: ``device`` (torch device), ``pg_fp64`` (validation precision for PG draws).
+            Engine knobs: ``device`` (torch device), ``pg_fp64`` (validation precision for the PG / truncated-
+            normal draws), ``gram_int8`` (LogitRSR: exact INT8 slice GEMMs for the Omega-weighted Gram).
 
         Returns
         -------

@@ -80,8 +80,9 @@ def test_beta_draw_vs_reference_golden_via_huge_precision():
     eng.close()
 
 
-@pytest.mark.parametrize('q,chains', [(7, 5), (64, 130), (230, 3)])   # q = 230: the solve works out of global scratch
-def test_full_iteration_pieces_vs_oracle(q, chains):
+@pytest.mark.parametrize('q,chains,gram_int8', [(7, 5, False), (64, 130, False), (230, 3, False),   # q = 230: global-scratch solve
+                                                 (7, 5, True), (64, 130, True)])                      # exact INT8 slice-GEMM Gram
+def test_full_iteration_pieces_vs_oracle(q, chains, gram_int8):
     """Random states, several chains (incl. a padded tail and > 1 chain tile): every system of the Gaussian
     half and the z probabilities agree with the oracle to 1e-10."""
     from occuspytial_b200 import LogitRSRGibbs, _lib
@@ -93,7 +94,7 @@ def test_full_iteration_pieces_vs_oracle(q, chains):
     prob = s._problem_arrays()
     V, r, p, n = prob['W_rows'].shape[0], 3, 4, f.n
     rng = np.random.default_rng(5)
-    eng = s._make_engine(chains, seed=11, debug=True)
+    eng = s._make_engine(chains, seed=11, debug=True, gram_int8=gram_int8)
     st = dict(alpha=rng.normal(size=(chains, r)), beta=rng.normal(size=(chains, p)), tau=rng.uniform(0.3, 3, chains),
               eta=rng.normal(size=(chains, q)))
     eng.set_start(st)

@@ -225,6 +225,6 @@ def test_abi_library_exports_every_declared_symbol():
     P = _lib.Problem()
     assert _lib.load().occu_workspace_bytes(ctypes.byref(P)) == 0
     assert b'ABI version' in _lib.load().occu_last_error()
-    P.abi_version, P.model, P.n, P.p, P.r, P.q, P.V, P.chains = 1, 0, 1000, 3, 3, 64, 2500, 4096
+    P.abi_version, P.model, P.n, P.p, P.r, P.q, P.V, P.chains = _lib.ABI_VERSION, 0, 1000, 3, 3, 64, 2500, 4096
     nbytes = _lib.load().occu_workspace_bytes(ctypes.byref(P))
     assert 2e8 < nbytes < 2e9
