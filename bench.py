@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = 'chain-iterations/sec, LogitRSRGibbs n=10k sites, 4096 chains, 1/2/4/8 B200'
+GRAM = {'auto': None, 'dmma': False, 'int8': True}
 
 
 def parse():
@@ -38,8 +39,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--pg-fp64', action='store_true')
-    ap.add_argument('--gram', default='dmma', choices=['dmma', 'int8'],
-                    help='Omega-weighted Gram: hand-written FP64 DMMA kernel (default) or exact INT8 slice GEMMs')
+    ap.add_argument('--gram', default='auto', choices=['auto', 'dmma', 'int8'],
+                    help='Omega-weighted Gram: exact INT8 slice GEMMs, hand-written FP64 DMMA kernel, or the engine default')
     return ap.parse_args()
 
 
@@ -198,7 +199,7 @@ def run_b200(args):
     seed = 12345
     start = sampler._start_arrays(chains_total, None)
     start = {k: v[lo:lo + args.chains] for k, v in start.items()}
-    eng = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=args.gram == 'int8')
+    eng = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
     eng.set_start(start)
     rec = eng.alloc_record(args.steps)
     fails = eng.sweep(args.warmup)
@@ -230,6 +231,7 @@ def run_b200(args):
     eng.sweep(min(args.steps, 10))
     kms = eng.kernel_ms()
     eng.set_profiling(False)
+    gram_path = 'int8' if eng.gram_int8 else 'dmma'
     # the only cross-GPU exchange of the method: all-gather of per-chain summary blocks for R-hat / ESS
     lib = _lib.load()
     max_lag = min(args.steps - 1, 20)
@@ -242,6 +244,21 @@ def run_b200(args):
     eng.close()
     del eng, rec
     torch.cuda.empty_cache()
+    # the hand-written FP64 DMMA Gram kernel, measured beside the default path (rank 0 only, short run)
+    dmma_info = None
+    if gram_path == 'int8' and rank == 0:
+        e2 = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=False)
+        e2.set_start(start)
+        e2.sweep(5)
+        e2.set_profiling(True)
+        e2.sweep(8)
+        k2 = e2.kernel_ms()
+        e2.close()
+        del e2
+        torch.cuda.empty_cache()
+        g_ms = k2['gram_gemm'][0] / k2['gram_gemm'][1]
+        dmma_info = {'kernel': "dgemm::gemm_tn_kernel (hand-written FP64 DMMA Gram, gram='dmma' path)", 'ms_per_launch': g_ms,
+                     'step_ms_with_this_path': sum(v[0] / max(v[1], 1) for v in k2.values())}
 
     # ---- end to end through the public API: host data in, host draws out ----
     e2e = None
@@ -251,7 +268,7 @@ def run_b200(args):
             dist.barrier()
         t0 = time.perf_counter()
         post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, chains=chains_total, progressbar=False,
-                              pg_fp64=args.pg_fp64, gram_int8=args.gram == 'int8')
+                              pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         st = sampler._last_stats
@@ -271,17 +288,15 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the Gram GEMM on the FP64 tensor pipe ----
+    # ---- roofline of the dominant step: the Omega-weighted Gram ----
     pq = wl['p'] + wl['q']
     n_pad = -(-wl['n'] // 128) * 128
-    Cp = -(-args.chains // 128) * 128
-    ldg = -(-(pq * (pq + 1) // 2) // 128) * 128 + -(-pq // 128) * 128
+    M = pq * (pq + 1) // 2
+    M_pad = -(-M // 64) * 64
     gram_ms, gram_calls = kms['gram_gemm']
-    gram_flops_alg = 2.0 * wl['n'] * (pq * (pq + 1) / 2 + pq) * args.chains      # algorithmic
-    gram_tflops = gram_flops_alg / (gram_ms / gram_calls * 1e-3) / 1e12
+    gram_ms /= gram_calls
+    gram_flops_alg = 2.0 * wl['n'] * (M + pq) * args.chains      # algorithmic FP64 flops
     peak64 = fp64_peak_tflops(torch)
-    site_ms, site_calls = kms['site_pass']
-    site_bytes_alg = (8 + 8 + 8 + 2) * wl['n'] * args.chains      # psi in, omega + kd out, z in/out
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -289,23 +304,44 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     total_ms = sum(v[0] / max(v[1], 1) for v in kms.values())
+    if gram_path == 'int8':
+        # executed INT8 operations: 27 slice pairs of [chains x M_pad x n_pad] plus the 6 H slices
+        int8_ops = 2.0 * args.chains * n_pad * (27 * M_pad + 6 * (-(-pq // 64) * 64))
+        int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
+        roofline = {'bound': 'tensor', 'kernel': 'Gram step, INT8 path: slice_a_kernel + 8 cuBLASLt IMMA GEMMs (27 slice '
+                    'pairs) + combine kernels; exact integer evaluation of the FP64 contraction (gram_int8.cuh)',
+                    'achieved': int8_ops / (gram_ms * 1e-3) / 1e12, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
+                    'frac': int8_ops / (gram_ms * 1e-3) / 1e12 / int8_peak, 'traffic': None,
+                    'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (no INT8 figure is recorded; nominal dense INT8 is 4500)',
+                    'fp64_equivalent_tflops': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'fp64_dgemm_peak_tflops': peak64,
+                    'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
+    else:
+        roofline = {'bound': 'tensor', 'kernel': "dgemm::gemm_tn_kernel (Gram [Omega' Z | kd' U], FP64 DMMA)",
+                    'achieved': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+                    'frac': gram_flops_alg / (gram_ms * 1e-3) / 1e12 / peak64, 'traffic': None,
+                    'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, measured in this run (MEASURED_PEAKS.json '
+                                   'holds no FP64 figure)',
+                    'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
+    site_ms, site_calls = kms['site_pass']
+    site_bytes_alg = (8 + 8 + 8 + 2) * wl['n'] * args.chains      # psi in, omega + kd out, z in/out
     line = {
         'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(args, wl),
-        'clocks': clock_info, 'gpu_launches': int(launches), 'failed_chains': int(fails),
-        'roofline': {'bound': 'tensor', 'kernel': 'dgemm::gemm_tn_kernel (Gram [Omega\' Z | kd\' U], FP64 DMMA)',
-                     'achieved': gram_tflops, 'peak': peak64, 'unit': 'TFLOP/s', 'frac': gram_tflops / peak64,
-                     'traffic': None,
-                     'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, measured in this run (MEASURED_PEAKS.json '
-                                    'holds no FP64 figure)',
-                     'ms_per_launch': gram_ms / gram_calls, 'share_of_step': (gram_ms / gram_calls) / total_ms},
+        'clocks': clock_info, 'gpu_launches': int(launches), 'failed_chains': int(fails), 'gram_path': gram_path,
+        'roofline': roofline,
         'kernels_ms_per_step': {k: v[0] / max(v[1], 1) for k, v in kms.items()},
         'roofline_site_pass': {'bound': 'hbm', 'achieved': site_bytes_alg / (site_ms / site_calls * 1e-3) / 1e9,
                                'peak': hbm_peak, 'unit': 'GB/s',
                                'frac': site_bytes_alg / (site_ms / site_calls * 1e-3) / 1e9 / hbm_peak,
+                               'note': 'the site pass is instruction-issue bound (PG sampling), not HBM bound',
                                'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'},
     }
+    if dmma_info:
+        tf = gram_flops_alg / (dmma_info['ms_per_launch'] * 1e-3) / 1e12
+        dmma_info.update({'bound': 'tensor', 'achieved': tf, 'peak': peak64, 'unit': 'TFLOP/s', 'frac': tf / peak64,
+                          'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, measured in this run'})
+        line['roofline_dmma'] = dmma_info
     if e2e:
         line['e2e'] = e2e
     if not args.no_cpu_baseline and world == 1:

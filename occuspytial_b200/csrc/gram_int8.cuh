@@ -21,7 +21,10 @@
 
 namespace gint8 {
 
-constexpr int SA = 7, SB = 6, LMAX = 8;
+#ifndef GINT8_LMAX
+#define GINT8_LMAX 8
+#endif
+constexpr int SA = 7, SB = 6, LMAX = GINT8_LMAX;
 constexpr int MAX_JOBS = 32;
 constexpr double OMEGA_SCALE = 8.0;  // omega / 8 < 1: P(PG(1, c) > 8) < 1e-17 per draw; larger values saturate
 

@@ -69,6 +69,7 @@ class DeviceEngine:
             P.chains, P.chain_offset = self.chains, int(chain_offset)
             P.debug, P.pg_fp64 = int(bool(debug)), int(bool(pg_fp64))
             P.gram_int8 = int(bool(gram_int8))
+            self.gram_int8 = bool(gram_int8) and model == 'logit_rsr'
             P.icar_bw = int(problem.get('icar_bw', 0))
             P.seed = int(seed) & (2**64 - 1)
             P.X = up('X', X, np.float64)

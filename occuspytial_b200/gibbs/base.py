@@ -179,12 +179,28 @@ class GibbsBase:
                     site_class=f.site_class, tau_rate=f.tau_rate, tau_shape=f.tau_shape,
                     a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
 
-    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=False):
+    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=None):
+        """Engine for ``chains`` chains.  ``gram_int8``: True / False force the Gram path of LogitRSR (exact INT8
+        slice GEMMs / hand-written FP64 DMMA kernel); None picks INT8 when the problem is large enough for the
+        tensor-core path to pay (>= 1024 sites; the rule must not depend on the number of chains, or a shard of a
+        job would round differently from the whole job) and falls back to the DMMA kernel -- another GPU kernel
+        of this engine, not a CPU path -- if cuBLASLt offers no INT8 algorithm for the shape."""
         from ..engine import DeviceEngine
+        from .._lib import EngineError
         if self._model is None:
             raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
-        return DeviceEngine(self._model, self._problem_arrays(), chains, seed, chain_offset=chain_offset,
-                            device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8)
+        auto = gram_int8 is None
+        if auto:
+            gram_int8 = self._model == 'logit_rsr' and self.fixed.n >= 1024
+        problem = self._problem_arrays()
+        try:
+            return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8)
+        except EngineError as exc:
+            if not (auto and gram_int8 and 'INT8' in str(exc)):
+                raise
+            return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=False)
 
     def step(self):
         """Step through one iteration of the sampler.
@@ -214,7 +230,7 @@ class GibbsBase:
             self.state.k = self.state.z - 0.5
 
     def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None,
-                      pg_fp64=False, gram_int8=False):
+                      pg_fp64=False, gram_int8=None):
         """All chains of this process in lock-step on one device; returns the list of ``Chain`` views.
 
         Under torch.distributed the global ``chains`` are sharded contiguously over ranks and only the
