@@ -24,7 +24,7 @@
 #include "../../include/occu_b200.h"
 #include "common.cuh"
 #include "gemm_dmma.cuh"
-#include "gram_int8.cuh"
+#include "gram_tc.cuh"
 #include "samplers.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -57,7 +57,7 @@ constexpr int SITE_TILE = SITE_TILE_N;
 constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
 constexpr int SOLVE_THREADS = 128;
 constexpr int MAX_SMALL = 32;    // max p and r
-constexpr size_t LT_WS_BYTES = 64u << 20;  // cuBLASLt workspace of the INT8 Gram path
+constexpr int TC_BN = gtc::BN_DEFAULT;  // Z columns per tile of the tcgen05 Gram (6 level accumulators side by side in TMEM)
 
 struct Control {
     uint32_t iter;     // iteration counter (Philox coordinate)
@@ -97,17 +97,17 @@ struct View {
     double* apart;  // [n_tiles][NV][Cp]
     double* asum;   // [NV][Cp]
     double* gam;    // [Cp]  Gamma(tau_shape, 1) variates of this iteration
-    // optional exact-integer Gram path (gram_int8.cuh)
-    int int8;               // 1: G and H come from INT8 slice GEMMs
-    int n_jobs;
-    int8_t* Aq;             // [Cp][SA][n_pad]   base-128 digits of omega / 8
-    int8_t* k2q;            // [Cp][n_pad]       2 (z - 1/2)
-    int8_t* Bq;             // [ldz][SB][n_pad]  balanced base-128 digits of [Z | U] / column scale, reversed slice order
-    double* bscale;         // [ldz]
-    int32_t* Cbuf;          // [n_jobs][Cp][M_pad]
-    int32_t* Hbuf;          // [Cp][ldh * SB]
-    int* job_levels;        // [MAX_JOBS]
-    void* lt_ws;            // cuBLASLt workspace
+    // exact-integer Gram path on the tcgen05 tensor cores (gram_tc.cuh)
+    int int8;               // 1: G and H come from the tcgen05 kind::i8 slice kernel
+    int tc_Kp, tc_nsplit, tc_Mrows;
+    uint8_t* Aq;            // [SA + 1][Cp][tc_Kp]   base-256 digits of omega / 8, then z
+    int8_t* Bq;             // [SB][tc_Mrows][tc_Kp] balanced base-256 digits of [Z | U] / column scale
+    double* bscale;         // [ldz]       power-of-two column scales
+    double* tscale;         // [tc_Mrows]  output scale per sliced row: 8 c_m (Gram columns), c_a (U columns)
+    double* hshift;         // [ldh]       -colsum(U) / 2:  U'(z - 1/2) = U'z + hshift
+    double* Gp;             // [tc_nsplit][Cp][M_pad] K-chunk partials (tc_nsplit > 1 only)
+    double* Hp;             // [tc_nsplit][Cp][ldh]
+    int* tc_err;            // barrier-timeout flag of the tcgen05 kernel
     double* solve_scratch;  // [Cp][solve_stride] working set of the RSR solve when it exceeds shared memory, else NULL
     size_t solve_stride;    // doubles per chain (0: shared-memory path)
     double* zprob;  // [n][Cp] or NULL
@@ -133,9 +133,11 @@ struct occu_engine {
     long long launches;
     char* ws;
     size_t ws_bytes;
-    cublasLtHandle_t lt;
-    gint8::Plan plan;
-    gint8::LtGemm job_gemm[gint8::MAX_JOBS], h_gemm;
+    gtc::Geometry geo;
+    int sm_count;
+    CUtensorMap tmA, tmB;
+    bool slices_valid;      // Aq holds the digits of the current (omega, z)
+    bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines)
     int profiling;
     double kernel_ms[KC_COUNT];
     long long kernel_calls[KC_COUNT];
@@ -197,7 +199,10 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     v.int8 = (P->gram_int8 && P->model == OCCU_LOGIT_RSR) ? 1 : 0;
     if (v.int8) {
         v.ksplit = 1;
-        v.n_jobs = gint8::make_plan(v.n_pad).njobs;
+        const gtc::Geometry g = gtc::make_geometry(v.n, v.Cp, v.M, v.pq, TC_BN);
+        v.tc_Kp = g.Kp;
+        v.tc_nsplit = g.nsplit;
+        v.tc_Mrows = g.Mrows;
     }
     if (P->model == OCCU_PROBIT_RSR) {
         // only the K-split product U'd runs: split it until the grid covers the GPU (2 CTAs x 148 SMs)
@@ -243,7 +248,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.tau = c.take<double>(Cp);
     v.psi = c.take<double>((size_t)v.n_pad * Cp);
     v.omega = c.take<double>((size_t)v.n_pad * Cp);
-    v.kd = c.take<double>((size_t)v.n_pad * Cp);
+    v.kd = v.int8 ? nullptr : c.take<double>((size_t)v.n_pad * Cp);  // the tcgen05 Gram reads z as a byte plane instead
     v.z = c.take<uint8_t>((size_t)v.n * Cp);
     const bool probit = v.model == OCCU_PROBIT_RSR;
     v.G = (probit || icar) ? nullptr : c.take<double>(Cp * (size_t)v.M_pad);
@@ -255,14 +260,14 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.gam = c.take<double>(Cp);
     v.solve_scratch = v.solve_stride ? c.take<double>(Cp * v.solve_stride) : nullptr;
     if (v.int8) {
-        v.Aq = c.take<int8_t>(Cp * (size_t)gint8::SA * v.n_pad);
-        v.k2q = c.take<int8_t>(Cp * (size_t)v.n_pad);
-        v.Bq = c.take<int8_t>((size_t)v.ldz * gint8::SB * v.n_pad);
+        v.Aq = c.take<uint8_t>((size_t)(gtc::SA + 1) * Cp * v.tc_Kp);
+        v.Bq = c.take<int8_t>((size_t)gtc::SB * v.tc_Mrows * v.tc_Kp);
         v.bscale = c.take<double>(v.ldz);
-        v.Cbuf = c.take<int32_t>((size_t)v.n_jobs * Cp * v.M_pad);
-        v.Hbuf = c.take<int32_t>(Cp * (size_t)v.ldh * gint8::SB);
-        v.job_levels = c.take<int>(gint8::MAX_JOBS);
-        v.lt_ws = c.take<char>(LT_WS_BYTES);
+        v.tscale = c.take<double>(v.tc_Mrows);
+        v.hshift = c.take<double>(v.ldh);
+        v.Gp = v.tc_nsplit > 1 ? c.take<double>((size_t)v.tc_nsplit * Cp * v.M_pad) : nullptr;
+        v.Hp = v.tc_nsplit > 1 ? c.take<double>((size_t)v.tc_nsplit * Cp * v.ldh) : nullptr;
+        v.tc_err = c.take<int>(1);
     }
     v.zprob = debug ? c.take<double>((size_t)v.n * Cp) : nullptr;
     v.status = c.take<int32_t>(Cp);
@@ -300,7 +305,7 @@ __global__ void reset_z_kernel(View v) {
     const int i = (int)(idx / v.Cp);
     const uint8_t zc = v.site_class[i] == OCCU_SITE_NOT_OBS ? 0 : 1;
     v.z[idx] = zc;
-    v.kd[idx] = (double)zc - 0.5;
+    if (v.kd) v.kd[idx] = (double)zc - 0.5;
 }
 
 __global__ void set_control_kernel(Control* c, uint32_t iter, int first, int rec_index, int clear_fails) {
@@ -363,7 +368,10 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 // Philox streams are keyed by (chain, visit row | site, iteration, stage), so the result does not
 // depend on how lanes interleave.
 // ------------------------------------------------------------------------------------------------
-template <int R, typename PGT>
+//  SLICES (tcgen05 Gram path): phase 3 writes omega as SA base-256 digits of its 48-bit fixed-point value and z as one
+//          more byte plane, site-contiguous per chain (gram_tc.cuh: Aq[s][chain][site]) -- the A operand of the Gram
+//          kernel, 7 bytes per site instead of the two FP64 arrays omega and kd; a debug engine also writes omega.
+template <int R, typename PGT, bool SLICES>
 __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     extern __shared__ __align__(16) unsigned char site_smem[];
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
                 zc = g.unif_d() < pr ? 1 : 0;  // logit.py:246 / 250
             }
             v.z[off] = (uint8_t)zc;
-            v.kd[off] = (double)zc - 0.5;  // logit.py:252
+            if (!SLICES) v.kd[off] = (double)zc - 0.5;  // logit.py:252
         }
         zbits |= (uint64_t)zc << (i - i0);
         arg_s[i - i0][tid] = (PGT)psi;
@@ -489,8 +497,38 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
         }
     }
 
-    // ---- phase 3: coalesced write-out ----
-    for (int ii = i0; ii < i1; ii++) v.omega[(size_t)ii * Cp + c] = (double)arg_s[ii - i0][tid];
+    // ---- phase 3: write-out ----
+    if (!SLICES || v.zprob)
+        for (int ii = i0; ii < i1; ii++) v.omega[(size_t)ii * Cp + c] = (double)arg_s[ii - i0][tid];
+    if (SLICES) {
+        static_assert(SITE_TILE % 16 == 0, "16 sites per 128-bit store");
+        const size_t plane = (size_t)Cp * v.tc_Kp;
+        uint8_t* row = v.Aq + (size_t)c * v.tc_Kp + i0;
+#pragma unroll 1
+        for (int g = 0; g < SITE_TILE / 16; g++) {
+            uint32_t w[gtc::SA + 1][4];
+#pragma unroll
+            for (int s = 0; s <= gtc::SA; s++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[s][k] = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int ii = g * 16 + j;
+                unsigned long long q = 0ull;
+                if (i0 + ii < i1) {
+                    const double x = (double)arg_s[ii][tid] * 35184372088832.0;  // omega 2^45 = (omega / 8) 2^48
+                    q = x >= 281474976710655.0 ? 281474976710655ull : (x > 0.0 ? (unsigned long long)x : 0ull);
+                }
+                const int sh = 8 * (j & 3);
+#pragma unroll
+                for (int s = 0; s < gtc::SA; s++) w[s][j >> 2] |= (uint32_t)((q >> (8 * (gtc::SA - 1 - s))) & 0xFFull) << sh;
+                w[gtc::SA][j >> 2] |= (uint32_t)((zbits >> ii) & 1ull) << sh;
+            }
+#pragma unroll
+            for (int s = 0; s <= gtc::SA; s++)
+                *reinterpret_cast<uint4*>(row + (size_t)s * plane + g * 16) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
 }
@@ -2121,7 +2159,7 @@ __global__ void __launch_bounds__(128, 5) solve_logit_icar_mma_kernel(const View
 // ------------------------------------------------------------------------------------------------
 // host-side drivers
 // ------------------------------------------------------------------------------------------------
-template <typename PGT>
+template <typename PGT, bool SLICES>
 static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
@@ -2130,8 +2168,8 @@ static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
 #define CASE(R)                                                                                                      \
     case R:                                                                                                          \
         if (smem > 48 * 1024)                                                                                        \
-            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        site_pass_logit_kernel<R, PGT><<<grid, CHAIN_TILE, smem, st>>>(v);                                            \
+            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT, SLICES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        site_pass_logit_kernel<R, PGT, SLICES><<<grid, CHAIN_TILE, smem, st>>>(v);                                    \
         break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
@@ -2153,10 +2191,16 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
 #undef CASE
         }
         e->launches++;
+    } else if (v.int8) {
+        // the site pass writes the digits of (omega, z) for the tcgen05 Gram itself
+        if (e->pg_fp64) launch_site_pass_logit<double, true>(e, st);
+        else launch_site_pass_logit<float, true>(e, st);
+        e->slices_valid = true;
+        e->omega_in_slices = v.zprob == nullptr;
     } else if (e->pg_fp64) {
-        launch_site_pass_logit<double>(e, st);
+        launch_site_pass_logit<double, false>(e, st);
     } else {
-        launch_site_pass_logit<float>(e, st);
+        launch_site_pass_logit<float, false>(e, st);
     }
 }
 
@@ -2190,38 +2234,40 @@ static int launch_psi_gemm(occu_engine* e, cudaStream_t st) {
     return 0;
 }
 
-// G and H through INT8 slice GEMMs (gram_int8.cuh)
-static int launch_gram_int8(occu_engine* e, cudaStream_t st) {
+// G and H on the tcgen05 tensor cores (gram_tc.cuh).  The site pass of a sweep writes the digits of (omega, z)
+// itself; when omega or z were set from outside (debug / test hooks) they are sliced here first.
+static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
-    gint8::slice_a_kernel<<<dim3(v.n_pad / 32, v.Cp / 32), 256, 0, st>>>(v.omega, v.kd, v.n, v.n_pad, v.Cp, v.Aq, v.k2q);
-    e->launches++;
-    const size_t job_stride = (size_t)v.Cp * v.M_pad;
-    for (int j = 0; j < e->plan.njobs; j++) {
-        const gint8::Job& jb = e->plan.jobs[j];
-        const int r0 = gint8::SB + 1 - jb.level + jb.s0;  // reversed slot of the first Z slice of this job (1-based)
-        const int8_t* X = v.Bq + (size_t)(r0 - 1) * v.n_pad;
-        const int8_t* Y = v.Aq + (size_t)(jb.s0 - 1) * v.n_pad;
-        if (gint8::lt_run(e->lt, e->job_gemm[j], X, Y, v.Cbuf + j * job_stride, v.lt_ws, LT_WS_BYTES, st) !=
-            CUBLAS_STATUS_SUCCESS)
-            return set_err("cublasLtMatmul (INT8 Gram) failed");
+    const gtc::Geometry& g = e->geo;
+    if (!e->slices_valid) {
+        gtc::slice_a_kernel<<<dim3((v.tc_Kp + 31) / 32, v.Cp / 32), 256, 0, st>>>(v.omega, v.z, v.n, v.tc_Kp, v.Cp, v.Aq);
         e->launches++;
+        e->slices_valid = true;
+        e->omega_in_slices = false;
     }
-    const int8_t* XU = v.Bq + (size_t)v.M_pad * gint8::SB * v.n_pad;
-    if (gint8::lt_run(e->lt, e->h_gemm, XU, v.k2q, v.Hbuf, v.lt_ws, LT_WS_BYTES, st) != CUBLAS_STATUS_SUCCESS)
-        return set_err("cublasLtMatmul (INT8 H) failed");
-    const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
-    gint8::combine_g_kernel<<<(unsigned)((tg + 255) / 256), 256, 0, st>>>(v.Cbuf, e->plan.njobs, v.job_levels, job_stride,
-                                                                          v.bscale, v.Cp, v.M_pad, v.G);
-    gint8::combine_h_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(v.Hbuf, v.bscale + v.M_pad, v.Cp, v.pq, v.ldh,
-                                                                          v.Hpart);
-    e->launches += 3;
+    gtc::Params p;
+    p.Cp = v.Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
+    p.n_gt = g.n_gt; p.n_ht = g.n_ht; p.Mrows = g.Mrows; p.M = v.M; p.pq = v.pq; p.ldg = v.M_pad; p.ldh = v.ldh;
+    p.scale = v.tscale; p.hshift = v.hshift; p.err = v.tc_err; p.mode = 0;
+    p.Gpart = g.nsplit > 1 ? v.Gp : v.G;
+    p.Hpart = g.nsplit > 1 ? v.Hp : v.Hpart;
+    const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
+    const int grid = nitems < e->sm_count ? nitems : e->sm_count;
+    gtc::gram_tc_kernel<TC_BN><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+    e->launches++;
+    if (g.nsplit > 1) {
+        const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
+        gtc::reduce_parts_kernel<<<(unsigned)((tg + 255) / 256), 256, 0, st>>>(v.Gp, g.nsplit, tg, tg, v.M_pad, v.M, v.G);
+        gtc::reduce_parts_kernel<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(v.Hp, g.nsplit, th, th, v.ldh, v.pq, v.Hpart);
+        e->launches += 2;
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
-    if (v.int8) return launch_gram_int8(e, st);
+    if (v.int8) return launch_gram_tc(e, st);
     dgemm::Args a;
     memset(&a, 0, sizeof(a));
     a.A1 = v.omega; a.B = v.ZU; a.Out = v.G;
@@ -2342,6 +2388,11 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     e->ws = (char*)workspace;
     e->ws_bytes = need;
     e->profiling = 0;
+    {
+        int dev = 0;
+        e->sm_count = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
     for (int k = 0; k < KC_COUNT; k++) { e->kernel_ms[k] = 0.0; e->kernel_calls[k] = 0; }
     for (int k = 0; k <= KC_COUNT; k++) e->ev[k] = nullptr;
 
@@ -2393,32 +2444,28 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         gram_unit_kernel<<<(v.M + 127) / 128, 128, 0, st>>>(v);
         e->launches++;
     }
-    e->lt = nullptr;
+    e->slices_valid = false;
+    e->omega_in_slices = false;
     if (v.int8) {
-        // slice [Z | U] once; plan the slice-pair GEMMs and let cuBLASLt pick an IMMA algorithm for each shape
-        gint8::column_scale_kernel<<<(v.ldz + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.ldz, v.bscale);
-        gint8::slice_b_kernel<<<dim3((v.n_pad + 255) / 256, v.ldz), 256, 0, st>>>(v.ZU, v.n, v.n_pad, v.ldz, v.ldz, v.bscale,
-                                                                                   v.Bq);
-        e->launches += 2;
-        e->plan = gint8::make_plan(v.n_pad);
-        int levels[gint8::MAX_JOBS] = {0};
-        for (int j = 0; j < e->plan.njobs; j++) levels[j] = e->plan.jobs[j].level;
-        FAIL_IF(cudaMemcpyAsync(v.job_levels, levels, sizeof(levels), cudaMemcpyHostToDevice, st));
-        FAIL_IF(cudaStreamSynchronize(st));
-        if (cublasLtCreate(&e->lt) != CUBLAS_STATUS_SUCCESS) {
-            delete e;
-            return set_err("cublasLtCreate failed");
-        }
-        const char* why = nullptr;
-        for (int j = 0; j < e->plan.njobs && !why; j++)
-            why = gint8::lt_setup(e->lt, e->job_gemm[j], v.M_pad, v.Cp, e->plan.jobs[j].npairs * v.n_pad,
-                                  (size_t)gint8::SB * v.n_pad, (size_t)gint8::SA * v.n_pad, v.M_pad, LT_WS_BYTES);
-        if (!why)
-            why = gint8::lt_setup(e->lt, e->h_gemm, v.ldh * gint8::SB, v.Cp, v.n_pad, v.n_pad, v.n_pad,
-                                  (size_t)v.ldh * gint8::SB, LT_WS_BYTES);
+        // slice [Z | U] once, encode the TMA descriptors of the two operand arrays
+        e->geo = gtc::make_geometry(v.n, v.Cp, v.M, v.pq, TC_BN);
+        const gtc::Geometry& g = e->geo;
+        gtc::column_scale_kernel<<<(v.ldz + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.ldz, v.bscale);
+        gtc::slice_b_kernel<<<dim3((g.Kp + 255) / 256, g.Mrows), 256, 0, st>>>(v.ZU, v.n, g.Kp, v.ldz, v.M, g.Mg_pad, v.pq, v.M_pad,
+                                                                               g.Mrows, v.bscale, v.tscale, v.Bq);
+        gtc::hshift_kernel<<<(v.ldh + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.M_pad, v.pq, v.ldh, v.hshift);
+        e->launches += 3;
+        FAIL_IF(cudaMemsetAsync(v.Aq, 0, (size_t)(gtc::SA + 1) * v.Cp * g.Kp, st));
+        FAIL_IF(cudaMemsetAsync(v.G, 0, (size_t)v.Cp * v.M_pad * 8, st));
+        FAIL_IF(cudaMemsetAsync(v.tc_err, 0, sizeof(int), st));
+        const char* why = gtc::make_map(&e->tmA, v.Aq, (uint64_t)(gtc::SA + 1) * v.Cp, g.Kp, gtc::BM);
+        if (!why) why = gtc::make_map(&e->tmB, v.Bq, (uint64_t)gtc::SB * g.Mrows, g.Kp, TC_BN);
+        if (!why && cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess)
+            why = "cudaFuncSetAttribute(shared memory) failed";
         if (why) {
             occu_destroy(e);
-            return set_err("INT8 Gram path: cuBLASLt setup failed (%s)", why);
+            return set_err("INT8 Gram path: %s", why);
         }
     }
     const size_t total = (size_t)v.n * v.Cp;
@@ -2433,11 +2480,6 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
 
 void occu_destroy(occu_engine_t* eng) {
     if (!eng) return;
-    if (eng->lt) {
-        for (int j = 0; j < gint8::MAX_JOBS; j++) gint8::lt_destroy(eng->job_gemm[j]);
-        gint8::lt_destroy(eng->h_gemm);
-        cublasLtDestroy(eng->lt);
-    }
     for (int k = 0; k <= KC_COUNT; k++)
         if (eng->ev[k]) cudaEventDestroy(eng->ev[k]);
     delete eng;
@@ -2486,7 +2528,28 @@ static int field_info(const occu_engine* e, int field, void** ptr, int* d, int* 
 // kd must follow z when z is set from outside
 __global__ void kd_from_z_kernel(View v) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < (size_t)v.n * v.Cp) v.kd[idx] = (double)v.z[idx] - 0.5;
+    if (v.kd && idx < (size_t)v.n * v.Cp) v.kd[idx] = (double)v.z[idx] - 0.5;
+}
+
+// omega from its digits (tcgen05 Gram path: a non-debug site pass writes only the digits)
+__global__ void omega_from_slices_kernel(View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)v.n * v.Cp) return;
+    const size_t i = idx / v.Cp, c = idx % v.Cp;
+    const size_t plane = (size_t)v.Cp * v.tc_Kp;
+    unsigned long long q = 0ull;
+    for (int s = 0; s < gtc::SA; s++) q = (q << 8) | v.Aq[(size_t)s * plane + c * v.tc_Kp + i];
+    v.omega[idx] = (double)q * (1.0 / 35184372088832.0);
+}
+
+static int materialise_omega(occu_engine* e, cudaStream_t st) {
+    if (!(e->v.int8 && e->slices_valid && e->omega_in_slices)) return 0;
+    const size_t total = (size_t)e->v.n * e->v.Cp;
+    omega_from_slices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->v);
+    e->launches++;
+    e->omega_in_slices = false;
+    CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int occu_set_field(occu_engine_t* e, int field, const void* src, void* stream) {
@@ -2495,6 +2558,12 @@ int occu_set_field(occu_engine_t* e, int field, const void* src, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     void* ptr; int d, u8;
     if (field_info(e, field, &ptr, &d, &u8)) return -1;
+    if (field == OCCU_F_Z || field == OCCU_F_OMEGA) {
+        // the digits no longer describe (omega, z): the next Gram re-slices from the FP64 / u8 fields
+        if (field == OCCU_F_Z && materialise_omega(e, st)) return -1;
+        e->slices_valid = false;
+        e->omega_in_slices = false;
+    }
     const View& v = e->v;
     dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
     if (u8) to_chain_minor_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)src, (uint8_t*)ptr, v.C, v.Cp, d);
@@ -2514,6 +2583,7 @@ int occu_get_field(occu_engine_t* e, int field, void* dst, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     void* ptr; int d, u8;
     if (field_info(e, field, &ptr, &d, &u8)) return -1;
+    if (field == OCCU_F_OMEGA && materialise_omega(e, st)) return -1;
     const View& v = e->v;
     dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
     if (u8) to_chain_major_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)ptr, (uint8_t*)dst, v.C, v.Cp, d);
@@ -2530,6 +2600,8 @@ int occu_reset(occu_engine_t* e, void* stream) {
     const size_t total = (size_t)v.n * v.Cp;
     reset_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v);
     set_control_kernel<<<1, 1, 0, st>>>(v.ctl, 0u, 1, -1, 1);
+    e->slices_valid = false;
+    e->omega_in_slices = false;
     CUDA_OK(cudaMemsetAsync(v.status, 0, (size_t)v.Cp * 4, st));
     e->launches += 2;
     CUDA_OK(cudaGetLastError());

@@ -1,0 +1,624 @@
+// gram_tc.cuh -- the Omega-weighted Gram  G = Omega' Z  and  H = z' U  on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, TMEM accumulators, TMA-staged operands), hand-written for sm_100a.
+//
+// What it replaces: the two dgemm contractions of omega_b per iteration in the reference,
+//   K' diag(omega) K           occuspytial/gibbs/logit.py:327-335  (_EtaRSRPosterior.rvs)
+//   X' diag(omega) X           occuspytial/gibbs/logit.py:230      (_update_beta)
+// and the products K'k, X'k (logit.py:228, 481) -- all are columns of the joint Gram of U = [X K].
+//
+// FP64 has no tcgen05 kind, and the FP64 DMMA pipe tops out near 37 TFLOP/s.  The same FP64 contraction is
+// evaluated here by error-free integer slicing (Ozaki scheme) with base-256 digits:
+//     omega / 8       = sum_{s=1..SA} a_s 256^-s,   a_s in [0, 255]  (unsigned, 48 bits)
+//     Z[:, m] / c_m   = sum_{t=1..SB} b_t 256^-t,   b_t in [-128, 127]  (balanced signed digits of
+//                       rint(Z / c_m 2^(8 SB)), |Z / c_m| <= 0.495, c_m a power of two)
+//     G[c][m]         = 8 c_m  sum_{L = s + t <= LMAX} 256^-L  sum_i a_s[i][c] b_t[i][m]
+// Every inner sum is a u8 x s8/u8 -> s32 tensor-core product: exact and order-independent.  One CTA owns a
+// 128-chain x BN-column tile; the NLEV = LMAX - 1 levels are NLEV accumulators side by side in TMEM
+// (NLEV x BN <= 512 columns), so a stage of operands (SA omega slices + SB Z slices of one 64-byte K block) feeds
+// all NPAIR slice pairs: 2.7x more MMA work per staged byte than a plain GEMM tile.
+//
+// Shared-memory bandwidth is what bounds an SS-mode MMA this narrow (a 128 x 80 x 32 MMA reads 6.5 KB for 40
+// tensor-pipe cycles: 166 B/clk against the 128 B/clk the pipe can read -- measured: 72 % smem pipe, 55 % tensor
+// pipe).  The slices of Z are therefore stored t-major, [t][BN rows], so that the accumulators of CONSECUTIVE
+// levels s + 1, s + 2, ... are the product of ONE omega slice s with SEVERAL consecutive Z slices: one wide MMA
+// (N up to 256) replaces three or four and reads the omega tile once (110 B/clk).  Only the first K block of a
+// work item, where some accumulators of such a run start from zero and others do not, is issued pair by pair.
+//
+// K is cut into chunks short enough that no INT32 accumulator can overflow (5 pairs x 255 x 128 per site and
+// level => 13120 sites); a work item is (tile, chunk).  With one chunk the epilogue writes G and H directly,
+// otherwise each chunk writes its own partial and a fixed-order reduction follows.  The FP64 recombination
+// (sum_L 256^-L C_L, scaling by 8 c_m) happens in the epilogue straight from TMEM; no INT32 ever reaches HBM.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over work items):
+//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_64B boxes, 3-stage mbarrier ring)
+//   warp 1    MMA issuer    (one elected lane: 2 x NPAIR tcgen05.mma per stage, tcgen05.commit frees the stage)
+//   warps 2-5 epilogue      (tcgen05.ld 32x32b.x16 per level -> FP64 -> global)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gtc {
+
+#ifndef GTC_SB
+#define GTC_SB 6
+#endif
+constexpr int SA = 6;             // omega slices (unsigned bytes): 48-bit fixed point of omega / 8
+constexpr int SB = GTC_SB;        // Z slices (balanced signed bytes): 6 -> |error| <= 2^-49 c_m per entry, 5 -> 2^-41 c_m
+constexpr int LMAX = 7;           // keep slice pairs with s + t <= LMAX (dropped products are below 2^-56 of the scale)
+constexpr int NLEV = LMAX - 1;    // levels 2 .. LMAX
+constexpr int BM = 128;           // chains per tile (TMEM lanes)
+constexpr int BK = 64;            // bytes (= int8 elements) of K per stage, one SWIZZLE_64B row
+constexpr int BN_DEFAULT = SB == 6 ? 64 : 80;  // Z columns per tile: NLEV x BN TMEM columns, 3 stages within 227 KB
+constexpr int STAGES = 3;
+constexpr int A_SLOTS = SA;       // slot 0 doubles as the z slice for H tiles
+constexpr int A_TILE_BYTES = BM * BK;
+
+constexpr int THREADS = 192;
+constexpr double OMEGA_SCALE = 8.0;    // omega / 8 < 1: P(PG(1, c) > 8) < 1e-17 per draw; larger values saturate
+constexpr int Z_SLICE = SA;            // index of the z (occupancy, 0/1) slice in the A operand array
+
+__host__ __device__ constexpr int npairs() {
+    int c = 0;
+    for (int s = 1; s <= SA; s++)
+        for (int t = 1; t <= SB; t++) c += (s + t <= LMAX);
+    return c;
+}
+constexpr int NPAIR = npairs();
+// K blocks per chunk such that no INT32 accumulator can overflow: the fullest level holds min(SA, SB, LMAX - 1) pairs
+// of |a b| <= 255 x 128 per site  (SB = 6: 171 blocks = 10944 sites; SB = 5: 205 blocks = 13120 sites)
+__host__ __device__ constexpr int imin3(int a, int b, int c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
+constexpr int MAX_KB_PER_CHUNK = (int)(2147483647LL / (255LL * 128LL * imin3(SA, SB, LMAX - 1)) / 64);
+
+template <int BN>
+struct Cfg {
+    static_assert(BN % 16 == 0 && NLEV * BN <= 512, "accumulators must fit the 512 TMEM columns");
+    static constexpr int B_TILE_BYTES = BN * BK;
+    static constexpr int STAGE_BYTES = A_SLOTS * A_TILE_BYTES + SB * B_TILE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(SMEM_BYTES <= 227 * 1024, "stages must fit the 227 KB of shared memory a CTA can own");
+};
+
+struct Params {
+    int Cp;             // padded chains (multiple of 128)
+    int kblocks;        // number of 64-byte K blocks (Kp / 64)
+    int nsplit;         // K chunks
+    int kb_per_chunk;
+    int MT;             // chain tiles
+    int n_gt, n_ht;     // column tiles of the G part and of the H (U) part
+    int Mrows;          // rows of one Z slice = (n_gt + n_ht) BN
+    int M, pq;          // valid columns of G and H
+    int ldg, ldh;       // leading dimensions of the chain-major outputs
+    const double* scale;   // [Mrows]  8 c_m (G part) / c_a (H part)
+    const double* hshift;  // [>= pq] added to H (chunk 0): U'(z - 1/2) = U'z - colsum(U) / 2; may be NULL
+    double* Gpart;         // [nsplit][Cp][ldg]
+    double* Hpart;         // [nsplit][Cp][ldh]
+    int* err;              // set to 1 if a barrier wait times out (debug aid; 0 otherwise)
+    int mode;              // 0 = normal; bottleneck probes (results are garbage): 1 = no TMA loads, 2 = no MMAs
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers (raw PTX)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error shows up as a flagged trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++) {
+        if (spins > (1u << 28)) {
+            if (err) *err = 1;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major SWIZZLE_64B operand tile: rows of 64 bytes, 8-row groups 512 bytes apart (canonical layout
+// ((8,n),2):((4,SBO),1) in 16-byte units), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;              // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // version
+    d |= (uint64_t)4 << 61;                       // SWIZZLE_64B
+    return d;
+}
+// kind::i8 instruction descriptor: D = S32, A = u8 (K-major), B = s8 (K-major), M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_i8(int n) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Low word of a SWIZZLE_64B K-major descriptor; byte offsets inside a stage are added as (bytes >> 4).
+__device__ __forceinline__ uint32_t desc_lo_sw64(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO = 512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo) { return ((uint64_t)DESC_HI_SW64 << 32) | lo; }
+
+template <bool ACC>
+__device__ __forceinline__ void mma_i8_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+    }
+}
+
+// first (s, t) of a level in the issue order (s ascending, then t ascending)
+__host__ __device__ constexpr bool first_of_level(int s, int t) {
+    for (int s2 = 1; s2 <= SA; s2++)
+        for (int t2 = 1; t2 <= SB; t2++)
+            if (s2 + t2 == s + t && s2 + t2 <= LMAX) return s2 == s && t2 == t;
+    return false;
+}
+
+template <int BN, int S, int T, int K2, bool FIRST>
+__device__ __forceinline__ void issue_one_g(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    constexpr int lev = S + T - 2;
+    constexpr uint32_t aoff = ((S - 1) * A_TILE_BYTES + K2 * 32) >> 4;
+    constexpr uint32_t boff = ((T - 1) * BN * BK + K2 * 32) >> 4;
+    constexpr uint32_t id = idesc_i8(BN);
+    constexpr bool start = FIRST && K2 == 0 && first_of_level(S, T);
+    mma_i8_imm<!start>(tmem_base + lev * BN, desc_from(a_lo + aoff), desc_from(b_lo + boff), id);
+}
+template <int BN, bool FIRST, int S, int T>
+__device__ __forceinline__ void issue_pairs_g(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    if constexpr (S <= SA) {
+        if constexpr (S + T <= LMAX && T <= SB) {
+            issue_one_g<BN, S, T, 0, FIRST>(tmem_base, a_lo, b_lo);
+            issue_one_g<BN, S, T, 1, FIRST>(tmem_base, a_lo, b_lo);
+        }
+        if constexpr (T < SB) issue_pairs_g<BN, FIRST, S, T + 1>(tmem_base, a_lo, b_lo);
+        else issue_pairs_g<BN, FIRST, S + 1, 1>(tmem_base, a_lo, b_lo);
+    }
+}
+template <int BN, bool FIRST>
+__device__ __forceinline__ void issue_g(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    static_assert(BK == 64, "two K = 32 MMAs per stage");
+    issue_pairs_g<BN, FIRST, 1, 1>(tmem_base, a_lo, b_lo);
+}
+template <int BN, bool FIRST, int T>
+__device__ __forceinline__ void issue_pairs_h(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    if constexpr (T <= SB) {
+        constexpr uint32_t id = idesc_i8(BN);
+        constexpr uint32_t boff = ((T - 1) * BN * BK) >> 4;
+        mma_i8_imm<!FIRST>(tmem_base + (T - 1) * BN, desc_from(a_lo), desc_from(b_lo + boff), id);
+        mma_i8_imm<true>(tmem_base + (T - 1) * BN, desc_from(a_lo + 2), desc_from(b_lo + boff + 2), id);
+        issue_pairs_h<BN, FIRST, T + 1>(tmem_base, a_lo, b_lo);
+    }
+}
+template <int BN, bool FIRST>
+__device__ __forceinline__ void issue_h(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    issue_pairs_h<BN, FIRST, 1>(tmem_base, a_lo, b_lo);
+}
+
+// ---- wide runs (all K blocks but the first of a work item) ----
+template <int BN>
+__host__ __device__ constexpr int run_blocks() { return 256 / BN; }  // Z slices of BN rows one MMA can span (N <= 256)
+__host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
+
+// omega slice S (or the z slice for H tiles, A_OFF16 = 0) times Z slices T0 .. : accumulators of levels S + T0 - 2 ...
+template <int BN, int S, int T0, int TMAX, int K2, int LEV0>
+__device__ __forceinline__ void issue_run(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    if constexpr (T0 <= TMAX) {
+        constexpr int nb = imin(run_blocks<BN>(), TMAX - T0 + 1);
+        constexpr uint32_t aoff = ((S - 1) * A_TILE_BYTES + K2 * 32) >> 4;
+        constexpr uint32_t boff = ((T0 - 1) * BN * BK + K2 * 32) >> 4;
+        mma_i8_imm<true>(tmem_base + (LEV0 + T0 - 1) * BN, desc_from(a_lo + aoff), desc_from(b_lo + boff), idesc_i8(nb * BN));
+        issue_run<BN, S, T0 + nb, TMAX, K2, LEV0>(tmem_base, a_lo, b_lo);
+    }
+}
+template <int BN, int S, int K2>
+__device__ __forceinline__ void issue_slices_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    if constexpr (S <= SA) {
+        issue_run<BN, S, 1, imin(SB, LMAX - S), K2, S - 1>(tmem_base, a_lo, b_lo);  // level index of (S, 1) is S - 1
+        issue_slices_wide<BN, S + 1, K2>(tmem_base, a_lo, b_lo);
+    }
+}
+template <int BN>
+__device__ __forceinline__ void issue_g_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    issue_slices_wide<BN, 1, 0>(tmem_base, a_lo, b_lo);
+    issue_slices_wide<BN, 1, 1>(tmem_base, a_lo, b_lo);
+}
+template <int BN>
+__device__ __forceinline__ void issue_h_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
+    issue_run<BN, 1, 1, SB, 0, 0>(tmem_base, a_lo, b_lo);  // z slice sits in A slot 0; accumulator t - 1
+    issue_run<BN, 1, 1, SB, 1, 0>(tmem_base, a_lo, b_lo);
+}
+
+struct Item {
+    int mt, nt, kb0, kb1, chunk;
+    bool is_h;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int item) {
+    // G items first (all chain tiles of one column tile are adjacent so that a wave shares few Z tiles), the
+    // four-times cheaper H items last: they back-fill the tail of the last wave.
+    Item it;
+    const int per_tile = p.nsplit;
+    const int tile = item / per_tile;
+    it.chunk = item - tile * per_tile;
+    it.mt = tile % p.MT;
+    it.nt = tile / p.MT;
+    it.is_h = it.nt >= p.n_gt;
+    it.kb0 = it.chunk * p.kb_per_chunk;
+    it.kb1 = min(it.kb0 + p.kb_per_chunk, p.kblocks);
+    return it;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES] TMA -> MMA
+    uint64_t* empty = bars + STAGES;        // [STAGES] MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * STAGES + 1;  // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = p.MT * (p.n_gt + p.n_ht) * p.nsplit;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                const int arow = it.mt * BM;
+                const int brow = it.nt * BN;
+                const uint32_t bytes = (it.is_h ? A_TILE_BYTES : SA * A_TILE_BYTES) + SB * C::B_TILE_BYTES;
+                for (int kb = it.kb0; kb < it.kb1; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1, p.err);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sb = sa + A_SLOTS * A_TILE_BYTES;
+                    if (p.mode == 1) {
+                        mbar_arrive(&full[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
+                    mbar_expect_tx(&full[stage], bytes);
+                    if (it.is_h) {
+                        tma_load_2d(&tmA, &full[stage], sa, kb * BK, Z_SLICE * p.Cp + arow);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < SA; s++)
+                            tma_load_2d(&tmA, &full[stage], sa + s * A_TILE_BYTES, kb * BK, s * p.Cp + arow);
+                    }
+#pragma unroll
+                    for (int t = 0; t < SB; t++)
+                        tma_load_2d(&tmB, &full[stage], sb + t * C::B_TILE_BYTES, kb * BK, t * p.Mrows + brow);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // One lane issues everything.  The issue rate matters (one MMA is only 32-40 tensor-pipe cycles): the
+        // descriptors of a stage differ by compile-time offsets from one per-stage base, and whether an MMA starts
+        // its accumulator (first K block of the chunk) is a compile-time property of the unrolled pair list.
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                mbar_wait(tmem_empty, acc_phase ^ 1, p.err);  // epilogue has drained the accumulators
+                tc_fence_after();
+                for (int kb = it.kb0; kb < it.kb1; kb++) {
+                    mbar_wait(&full[stage], phase, p.err);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t a_lo = desc_lo_sw64(sa), b_lo = desc_lo_sw64(sa + A_SLOTS * A_TILE_BYTES);
+                    if (p.mode == 2) {
+                    } else if (it.is_h) {
+                        if (kb == it.kb0) issue_h<BN, true>(tmem_base, a_lo, b_lo);
+                        else issue_h_wide<BN>(tmem_base, a_lo, b_lo);
+                    } else {
+                        if (kb == it.kb0) issue_g<BN, true>(tmem_base, a_lo, b_lo);
+                        else issue_g_wide<BN>(tmem_base, a_lo, b_lo);
+                    }
+                    tc_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(tmem_full);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int quarter = warp & 3;  // TMEM lanes [32 quarter, 32 quarter + 32) are the ones this warp may read
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const Item it = decode_item(p, item);
+            mbar_wait(tmem_full, acc_phase, p.err);
+            tc_fence_after();
+            const int c = it.mt * BM + quarter * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            const int nlev = it.is_h ? SB : NLEV;
+            const int lev_w0 = it.is_h ? 1 : 2;  // weight of accumulator 0 is 256^-lev_w0
+            const int col0 = it.is_h ? (it.nt - p.n_gt) * BN : it.nt * BN;
+            const int ncols = it.is_h ? p.pq : p.M;
+            const int ld = it.is_h ? p.ldh : p.ldg;
+            double* out = (it.is_h ? p.Hpart + (size_t)it.chunk * p.Cp * p.ldh : p.Gpart + (size_t)it.chunk * p.Cp * p.ldg) +
+                          (size_t)c * ld;
+            const double* scale = p.scale + it.nt * BN;
+            const double* shift = (it.is_h && it.chunk == 0) ? p.hshift : nullptr;
+            for (int cg = 0; cg < BN / 16; cg++) {
+                double acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[j] = 0.0;
+                int32_t v[NLEV][16];
+#pragma unroll
+                for (int lev = 0; lev < NLEV; lev++)
+                    if (lev < nlev) tmem_ld16(trow + lev * BN + cg * 16, v[lev]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int lev = NLEV - 1; lev >= 0; lev--) {  // small terms first
+                    if (lev < nlev) {
+                        const double w = __longlong_as_double((long long)(1023 - 8 * (lev + lev_w0)) << 52);  // 256^-(lev + lev_w0)
+#pragma unroll
+                        for (int j = 0; j < 16; j++) acc[j] = fma((double)v[lev][j], w, acc[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int m = col0 + cg * 16 + j;
+                    if (m < ncols) out[m] = shift ? fma(acc[j], scale[cg * 16 + j], shift[m]) : acc[j] * scale[cg * 16 + j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// slicing kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+// c_m = 2^(e + 1) with max_i |Z[i][m]| = f 2^e, f in [0.5, 1) (one more doubling if f > 0.99)  =>  |Z / c_m| <= 0.495,
+// inside the range of SB balanced base-256 digits (127/255 = 0.498)
+__global__ void column_scale_kernel(const double* __restrict__ ZU, int n, int ld, int ncols, double* __restrict__ cscale) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ncols) return;
+    double mx = 0.0;
+    for (int i = 0; i < n; i++) mx = fmax(mx, fabs(ZU[(size_t)i * ld + m]));
+    int e = 0;
+    if (mx > 0.0) {
+        const double f = frexp(mx, &e);
+        e += f > 0.99 ? 2 : 1;
+    }
+    cscale[m] = ldexp(1.0, e);
+}
+
+// Bq[t][row][i]: balanced base-256 digits (each in [-128, 127]) of rint(Z[i][col] / c 2^(8 SB)); padding rows /
+// sites are zero.
+// row -> source column: rows [0, M) are the Gram columns, rows [Mg_pad, Mg_pad + pq) the U columns at src_u0 + a.
+__global__ void slice_b_kernel(const double* __restrict__ ZU, int n, int Kp, int ld, int M, int Mg_pad, int pq, int src_u0,
+                               int Mrows, const double* __restrict__ cscale, double* __restrict__ scale_out,
+                               int8_t* __restrict__ Bq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (i >= Kp || row >= Mrows) return;
+    int col = -1;
+    if (row < M) col = row;
+    else if (row >= Mg_pad && row < Mg_pad + pq) col = src_u0 + (row - Mg_pad);
+    long long q = 0;
+    if (col >= 0) {
+        const double c = cscale[col];
+        if (i == 0) scale_out[row] = row < M ? OMEGA_SCALE * c : c;
+        if (i < n) {
+            const double y = ZU[(size_t)i * ld + col] / c * (double)(1LL << (8 * SB));  // exact: c is a power of two
+            q = llrint(y);
+        }
+    } else if (i == 0) {
+        scale_out[row] = 0.0;
+    }
+#pragma unroll
+    for (int t = SB; t >= 1; t--) {
+        const long long d = ((q + 128) & 0xFF) - 128;  // balanced digit; the carry goes into the next one and
+        q = (q - d) >> 8;                              // |q 2^-40| <= 0.495 leaves none out of the top digit
+        Bq[((size_t)(t - 1) * Mrows + row) * Kp + i] = (int8_t)d;
+    }
+}
+
+// Aq[s][c][i] = digit s+1 of floor(omega[i][c] 2^45) (48-bit fixed point of omega / 8), Aq[Z_SLICE][c][i] = z[i][c].
+// 32 x 32 tile transpose from the chain-minor layout of the sweep state.
+__global__ void __launch_bounds__(256) slice_a_kernel(const double* __restrict__ omega, const uint8_t* __restrict__ z, int n,
+                                                      int Kp, int Cp, uint8_t* __restrict__ Aq) {
+    __shared__ uint8_t tile[SA + 1][32][36];
+    const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, c = c0 + tx;
+        unsigned long long q = 0;
+        uint8_t zz = 0;
+        if (i < n) {
+            const double x = omega[(size_t)i * Cp + c] * 35184372088832.0;  // 2^45
+            q = x >= 281474976710655.0 ? 281474976710655ull : (x > 0.0 ? (unsigned long long)x : 0ull);
+            zz = z[(size_t)i * Cp + c];
+        }
+#pragma unroll
+        for (int s = 0; s < SA; s++) tile[s][tx][r] = (uint8_t)(q >> (8 * (SA - 1 - s)));
+        tile[SA][tx][r] = zz;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * (SA + 1) * 8; idx += 256) {
+        const int w4 = idx & 7, rest = idx >> 3;
+        const int cc = rest & 31, s = rest >> 5;
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(&tile[s][cc][w4 * 4]);
+        if (i0 + w4 * 4 < Kp)
+            *reinterpret_cast<uint32_t*>(Aq + ((size_t)s * Cp + c0 + cc) * Kp + i0 + w4 * 4) = word;
+    }
+}
+
+// hshift[a] = -1/2 sum_i U[i][a] (fixed order), U = columns [u0, u0 + pq) of ZU
+__global__ void hshift_kernel(const double* __restrict__ ZU, int n, int ld, int u0, int pq, int ldh, double* __restrict__ hshift) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= ldh) return;
+    double acc = 0.0;
+    if (a < pq)
+        for (int i = 0; i < n; i++) acc += ZU[(size_t)i * ld + u0 + a];
+    hshift[a] = -0.5 * acc;
+}
+
+// out[c][m] = sum_chunks part[chunk][c][m] in chunk order (fixed order => deterministic)
+__global__ void reduce_parts_kernel(const double* __restrict__ part, int nsplit, size_t stride, size_t count, int ld, int ncols,
+                                    double* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int m = (int)(idx % ld);
+    double acc = 0.0;
+    if (m < ncols) {
+        for (int k = 0; k < nsplit; k++) acc += part[(size_t)k * stride + idx];
+    }
+    out[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D byte matrix [rows][Kp], box = 64 bytes x box_rows, SWIZZLE_64B
+inline const char* make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t Kp, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return "cuTensorMapEncodeTiled entry point not found";
+    const cuuint64_t dims[2] = {Kp, rows};
+    const cuuint64_t strides[1] = {Kp};
+    const cuuint32_t box[2] = {BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
+}
+
+struct Geometry {
+    int Kp, kblocks, nsplit, kb_per_chunk, MT, n_gt, n_ht, Mg_pad, Mrows;
+};
+inline Geometry make_geometry(int n, int Cp, int M, int pq, int BN, int want_split = 1) {
+    Geometry g;
+    g.Kp = (n + BK - 1) / BK * BK;
+    g.kblocks = g.Kp / BK;
+    g.nsplit = (g.kblocks + MAX_KB_PER_CHUNK - 1) / MAX_KB_PER_CHUNK;
+    if (g.nsplit < want_split) g.nsplit = want_split;  // more, shorter work items: better balance over the SMs
+    g.kb_per_chunk = (g.kblocks + g.nsplit - 1) / g.nsplit;
+    g.MT = Cp / BM;
+    g.n_gt = (M + BN - 1) / BN;
+    g.n_ht = (pq + BN - 1) / BN;
+    g.Mg_pad = g.n_gt * BN;
+    g.Mrows = (g.n_gt + g.n_ht) * BN;
+    return g;
+}
+
+}  // namespace gtc
