@@ -403,19 +403,20 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
             if (cls == OCCU_SITE_OBS) {
                 zc = 1;
             } else {
-                double pr = expit_d(psi);  // logit.py:241 / 249
+                // logit.py:241-245 / 249:  pr = expit(psi) prod / (1 - expit(psi) + expit(psi) prod) with
+                // prod = prod_j expit(-w_ij alpha)  ==  1 / (1 + exp(-psi) prod_j (1 + exp(w_ij alpha))): one exp per
+                // visit and one division per site; not-surveyed sites have the empty product
+                double grow = exp(-psi);
                 if (cls == OCCU_SITE_NOT_OBS) {
-                    double prod = 1.0;  // logit.py:242-243: prod_j expit(-w_ij alpha)
                     const int v1 = v.visit_ptr[i + 1];
                     for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
                         double lin = 0.0;
 #pragma unroll
                         for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
-                        prod *= expit_d(-lin);
+                        grow *= 1.0 + exp(lin);
                     }
-                    const double num = pr * prod;
-                    pr = num / ((1.0 - pr) + num);  // logit.py:244-245
                 }
+                const double pr = 1.0 / (1.0 + grow);
                 if (v.zprob) v.zprob[off] = pr;
                 Philox g;
                 g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
@@ -434,8 +435,11 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
     int i = i0 - 1, vv = 0, vend = 0, cur = 0;
     bool site_done = true, active = true, have = false, is_visit = false;
-    PGTask<PGT> task;
+    typename PGSel<PGT>::Task task;
     Philox g;
+    double wv[R];  // design row of the visit being drawn (kept from the fetch to the commit)
+#pragma unroll
+    for (int k = 0; k < R; k++) wv[k] = 0.0;
     while (__any_sync(0xffffffffu, active || have)) {
         if (!have && active) {
             // next draw of this lane's stream, loop-free: the visits of an occupied surveyed site
@@ -459,7 +463,10 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
                     cur = vv++;
                     double lin = 0.0;
 #pragma unroll
-                    for (int k = 0; k < R; k++) lin += v.W[(size_t)cur * R + k] * al[k];
+                    for (int k = 0; k < R; k++) {
+                        wv[k] = v.W[(size_t)cur * R + k];
+                        lin += wv[k] * al[k];
+                    }
                     carg = (PGT)lin;
                 } else {
                     site_done = true;
@@ -467,29 +474,27 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
                     carg = arg_s[i - i0][tid];
                 }
                 g.init(v.seed, gc, (uint32_t)cur, iter, is_visit ? ST_OMEGA_A : ST_OMEGA_B);
-                pg1_setup<PGT>(carg, task);   // one shared copy of the setup code for both kinds of draw
+                PGSel<PGT>::setup(carg, task);  // one shared copy of the setup code for both kinds of draw
                 have = true;
             }
         }
         if (have) {
             PGT ub, ux, u3, us, x;
             RT<PGT>::unif4(g, ub, ux, u3, us);
-            if (pg1_round<PGT>(task, ub, ux, u3, us, x)) {
+            if (PGSel<PGT>::round(task, ub, ux, u3, us, x)) {
                 have = false;
                 const double om = 0.25 * (double)x;
                 if (is_visit) {
-                    double w[R];
-#pragma unroll
-                    for (int k = 0; k < R; k++) w[k] = v.W[(size_t)cur * R + k];
                     const double yk = (double)v.y[cur] - 0.5;
                     int idx = 0;
 #pragma unroll
                     for (int a = 0; a < R; a++) {
+                        const double owa = om * wv[a];
 #pragma unroll
-                        for (int b = 0; b <= a; b++) acc[idx++] += om * w[a] * w[b];  // logit.py:222
+                        for (int b = 0; b <= a; b++, idx++) acc[idx] = fma(owa, wv[b], acc[idx]);  // logit.py:222
                     }
 #pragma unroll
-                    for (int a = 0; a < R; a++) acc[NA + a] += w[a] * yk;  // logit.py:223
+                    for (int a = 0; a < R; a++) acc[NA + a] = fma(wv[a], yk, acc[NA + a]);  // logit.py:223
                 } else {
                     arg_s[cur - i0][tid] = (PGT)om;
                 }
