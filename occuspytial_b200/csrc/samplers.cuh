@@ -107,6 +107,14 @@ __device__ __forceinline__ bool pg1_round(const PGTask<T>& s, T ub, T ux, T u3, 
 //     enters the loop.
 // The KS / moment tests against the oracle sampler arbitrate (tests/test_gpu_primitives.py).
 // ---------------------------------------------------------------------------------------------
+// MUFU approximations with flush-to-zero (one instruction each, <= 2 ulp; no IEEE fix-up or denormal paths)
+__device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_exp(float x) { return f_ex2(x * 1.4426950408889634f); }
+
 struct PGTaskF {
     float invK, p_right, rcp_left, mu, hz2;  // rcp_left = 1 / (1 - p_right)
     bool small_z;
@@ -117,51 +125,56 @@ __device__ __forceinline__ void pg1_setup_fast(float c, PGTaskF& s) {
     const float z = 0.5f * fabsf(c);
     s.hz2 = 0.5f * z * z;
     const float K = (float)(OCCU_PI * OCCU_PI / 8.0) + s.hz2;
-    s.invK = __frcp_rn(K);
+    s.invK = f_rcp(K);
     s.small_z = z * t < 1.0f;
-    s.mu = __frcp_rn(fmaxf(z, 1.0f));  // only used when z t >= 1 (z >= 1.5625)
-    const float two_k_over_pi = K * (float)(2.0 / OCCU_PI);
-    const float qdivp = s.small_z ? 0.42259909466742100f * two_k_over_pi * __expf(K * t)
-                                  : 2.0f * two_k_over_pi * __expf(K * t - z);
-    s.p_right = __frcp_rn(1.0f + qdivp);           // 0 when qdivp overflows
-    s.rcp_left = __frcp_rn(1.0f - s.p_right);
+    s.mu = f_rcp(fmaxf(z, 1.0f));  // only used when z t >= 1 (z >= 1.5625)
+    // q / p = (2K / pi) exp(K t) x { 4 Phi(-1.25)  |  2 exp(-z) }; overflow => p_right = 0
+    const float qdivp = K * (s.small_z ? (float)(0.42259909466742100 * 2.0 / OCCU_PI) : (float)(4.0 / OCCU_PI)) *
+                        f_exp(fmaf(K, t, s.small_z ? 0.0f : -z));
+    s.p_right = f_rcp(1.0f + qdivp);
+    s.rcp_left = f_rcp(1.0f - s.p_right);  // inf when p_right == 1 cannot happen: qdivp >= 0.33
 }
 
 __device__ __forceinline__ bool pg1_round_fast(const PGTaskF& s, float ub, float ux, float u3, float us, float& x) {
     const float t = (float)PG_TRUNC;
-    const float L = -__logf(ux);
+    const float L = -0.6931471805599453f * f_lg2(ux);
     bool pre = true;
-    float m2e;  // -2 e, e = pi^2 x / 2 (x > t) or 2 / x (x <= t): r_1 = 3 exp(-2 e)
+    float m2e;  // -2 e log2(e), e = pi^2 x / 2 (x > t) or 2 / x (x <= t): r_1 = 3 exp(-2 e)
     if (ub < s.p_right) {
         x = fmaf(L, s.invK, t);
-        m2e = -(float)(OCCU_PI * OCCU_PI) * x;
+        m2e = -(float)(OCCU_PI * OCCU_PI * 1.4426950408889634) * x;
     } else {
+        float rx;  // 1 / x
         if (s.small_z) {
             const float q2 = 2.0f * (L + 2.2476256772143173f);
-            const float q = q2 * rsqrtf(q2);
+            const float q = q2 * f_rsqrt(q2);
             const float num = fmaf(fmaf(fmaf(0.5547605086386899f, q, 2.046679917526049f), q, -0.8955289493983294f), q,
                                    -2.686210871246895f);
             const float den = fmaf(fmaf(0.55384050985106f, q, 2.090629666186503f), q, 1.0f);
-            const float ry = __fdividef(den, num);  // 1 / y
-            x = ry * ry;
-            pre = (x <= t) && (u3 <= __expf(-s.hz2 * x));
+            const float y = num * f_rcp(den);
+            rx = y * y;
+            x = f_rcp(rx);
+            pre = (x <= t) && (u3 <= f_exp(-s.hz2 * x));
         } else {
-            const float cs = __cosf(6.283185307179586f * u3);
+            const float cs = f_cos(6.283185307179586f * u3);
             const float w = s.mu * (2.0f * L * cs * cs);  // mu Y^2, Y ~ N(0,1)
             const float disc = fmaf(0.25f * w, w, w);
-            x = __fdividef(s.mu, 1.0f + 0.5f * w + disc * rsqrtf(fmaxf(disc, 1e-30f)));  // cancellation-free small root
+            const float root = fmaf(disc, f_rsqrt(fmaxf(disc, 1e-30f)), fmaf(0.5f, w, 1.0f));  // 1 + w/2 + sqrt(w + w^2/4)
+            // the two roots of Michael-Schucany-Haas are mu / root and mu root
             const float ur = (ub - s.p_right) * s.rcp_left;
-            if (ur * (s.mu + x) > s.mu) x = __fdividef(s.mu * s.mu, x);
+            const bool small_root = ur * (root + 1.0f) <= root;  // with probability mu / (mu + x), x = mu / root
+            x = small_root ? s.mu * f_rcp(root) : s.mu * root;
+            rx = f_rcp(x);
             pre = x <= t;
         }
-        m2e = __fdividef(-4.0f, x);
+        m2e = -4.0f * 1.4426950408889634f * rx;
     }
-    float sum = 1.0f - 3.0f * __expf(m2e);
+    float sum = fmaf(-3.0f, f_ex2(m2e), 1.0f);
     if (us <= sum) return pre;
     // rare: the first term did not decide
-    const float e = -0.5f * m2e;
+    const float e = -0.5f * 0.6931471805599453f * m2e;
     for (int n = 2;; n++) {
-        const float rn = (float)(2 * n + 1) * __expf(-(float)(n * (n + 1)) * e);
+        const float rn = (float)(2 * n + 1) * f_exp(-(float)(n * (n + 1)) * e);
         if (n & 1) {
             sum -= rn;
             if (us <= sum) return pre;
