@@ -60,7 +60,8 @@ def config_dict(args, wl):
                         f'V={wl["V"]} visit rows, RSR rank q={wl["q"]}, {args.chains} chains per GPU',
             'chains_per_gpu': args.chains, 'n_sites': wl['n'], 'rsr_rank_q': wl['q'], 'visit_rows': wl['V'],
             'parallelism': f'chains sharded over {args.gpus} GPU(s), no per-iteration collective',
-            'l2_policy': 'per-step working set (omega+psi+kd ~ 3 x n x chains x 8 B ~ 1 GB) exceeds the 126 MB L2'}
+            'l2_policy': 'per-step working set (psi 8 B + omega/z byte planes 7 B per site and chain ~ 0.6 GB, plus the '
+                         '0.25 GB of Z slices) exceeds the 126 MB L2'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -305,13 +306,23 @@ def run_b200(args):
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     total_ms = sum(v[0] / max(v[1], 1) for v in kms.values())
     if gram_path == 'int8':
-        # executed INT8 operations: 27 slice pairs of [chains x M_pad x n_pad] plus the 6 H slices
-        int8_ops = 2.0 * args.chains * n_pad * (27 * M_pad + 6 * (-(-pq // 64) * 64))
+        # executed INT8 operations of gram_tc_kernel (csrc/gram_tc.cuh): 21 slice pairs (6 omega x 6 Z slices, levels
+        # s + t <= 7) over 128-chain x 64-column tiles, plus the 6 slices of the U'z tiles
+        BN, PAIRS, SB = 64, 21, 6
+        Kp = -(-wl['n'] // 64) * 64
+        Cp = -(-args.chains // 128) * 128
+        int8_ops = 2.0 * Cp * Kp * BN * (-(-M // BN) * PAIRS + -(-pq // BN) * SB)
         int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
-        roofline = {'bound': 'tensor', 'kernel': 'Gram step, INT8 path: slice_a_kernel + 8 cuBLASLt IMMA GEMMs (27 slice '
-                    'pairs) + combine kernels; exact integer evaluation of the FP64 contraction (gram_int8.cuh)',
+        traffic = None
+        try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('gram_tc_kernel')
+        except (OSError, ValueError):
+            pass
+        roofline = {'bound': 'tensor', 'kernel': 'gtc::gram_tc_kernel<64>: hand-written tcgen05.mma kind::i8 (TMA-staged '
+                    'operands, 6 level accumulators in TMEM, FP64 recombination in the epilogue); exact integer evaluation '
+                    'of the FP64 contraction [Omega\' Z | z\' U] (csrc/gram_tc.cuh)',
                     'achieved': int8_ops / (gram_ms * 1e-3) / 1e12, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
-                    'frac': int8_ops / (gram_ms * 1e-3) / 1e12 / int8_peak, 'traffic': None,
+                    'frac': int8_ops / (gram_ms * 1e-3) / 1e12 / int8_peak, 'traffic': traffic,
                     'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (no INT8 figure is recorded; nominal dense INT8 is 4500)',
                     'fp64_equivalent_tflops': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'fp64_dgemm_peak_tflops': peak64,
                     'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
@@ -323,7 +334,8 @@ def run_b200(args):
                                    'holds no FP64 figure)',
                     'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
     site_ms, site_calls = kms['site_pass']
-    site_bytes_alg = (8 + 8 + 8 + 2) * wl['n'] * args.chains      # psi in, omega + kd out, z in/out
+    # psi in, z in/out, then omega + kd out (FP64 Gram path) or the 7 byte planes of (omega, z) (tcgen05 Gram path)
+    site_bytes_alg = (8 + 2 + (7 if gram_path == 'int8' else 16)) * wl['n'] * args.chains
     line = {
         'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

@@ -71,7 +71,7 @@ typedef struct {
     int32_t debug;        /* 1: keep occupancy probabilities / allow occu_debug_* */
     int32_t pg_fp64;      /* 1: PG / truncated-normal sampler transcendental work in FP64 (validation), 0: FP32 */
     int32_t icar_bw;      /* ICAR: half bandwidth of Q in the given site order; else 0 */
-    int32_t gram_int8;    /* LogitRSR: 1 = Omega-weighted Gram by exact INT8 slice GEMMs (gram_int8.cuh), 0 = FP64 DMMA */
+    int32_t gram_int8;    /* LogitRSR: 1 = Omega-weighted Gram on tcgen05 kind::i8 by exact integer slicing (gram_tc.cuh), 0 = FP64 DMMA */
     uint64_t seed;        /* Philox key (random_state of the sampler) */
     const double* X;      /* [n][p] */
     const double* K;      /* [n][q] RSR basis (fixed.K), NULL for ICAR */

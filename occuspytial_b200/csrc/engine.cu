@@ -10,7 +10,8 @@
 //   2. site pass: z | psi, alpha   (skipped at iteration 0: z comes from the data, base.py:113-118)
 //                 omega_a | z, alpha -> partial sums of W_e' Om_a W_e and W_e'(y_e - 1/2)
 //                 omega_b | psi                                       (logit.py:180-204, 234-252)
-//   3. [G | H] = [Omega' Z | kd' U]              DMMA GEMM            (logit.py:222-231, 327-335, 481)
+//   3. [G | H] = [Omega' Z | kd' U]              tcgen05 kind::i8 slice kernel (gram_tc.cuh; n >= 1024), else the
+//                                                FP64 DMMA GEMM      (logit.py:222-231, 327-335, 481)
 //   4. reduce the alpha partial sums (fixed order, no float atomics)
 //   5. per-chain solve: tau, eta, beta, alpha    (logit.py:206-232, 478-485; distributions.pyx:42-110)
 // The draw recorded after step 5 is (alpha, beta, tau) exactly as Chain.append sees it (base.py:238-239).
@@ -934,6 +935,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
     // ---- tau | eta   (logit.py:206-209) ----
     {
         double part = 0.0;
+#pragma unroll 8
         for (int idx = tid; idx < q * q; idx += T) {
             const int i = idx / q, j = idx - i * q;
             part += th[p + i] * v.Qrsr[idx] * th[p + j];
@@ -965,12 +967,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
         gx[idx] = i < q ? Grow[tri(p + i, a)] : 0.0;
     }
     __syncthreads();
-    for (int i = 0; i < q; i++) {  // row i of Lambda: contiguous in the packed Gram
-        const double* grow = Grow + tri(p + i, p);
-        double* brow = Bs + (i & 3) * 4;
-        const int I = i >> 2;
-        for (int j = tid; j <= i; j += T)
-            brow[bidx(I, j >> 2) + (j & 3)] = grow[j] + tau * v.Qrsr[(size_t)i * q + j];
+    {   // Lambda = K' Om K + tau Qrsr, flattened over the packed lower triangle so that every thread has several
+        // independent loads in flight (a row-by-row loop serialises 64 global-load latencies)
+        const int ntri = q * (q + 1) / 2;
+#pragma unroll 4
+        for (int t = tid; t < ntri; t += T) {
+            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (i * (i + 1) / 2 > t) i--;
+            while ((i + 1) * (i + 2) / 2 <= t) i++;
+            const int j = t - i * (i + 1) / 2;
+            Bs[bidx(i >> 2, j >> 2) + (i & 3) * 4 + (j & 3)] = Grow[tri(p + i, p + j)] + tau * v.Qrsr[(size_t)i * q + j];
+        }
     }
     for (int i = q + tid; i < q4; i += T) Bs[bidx(i >> 2, i >> 2) + (i & 3) * 5] = 1.0;  // identity padding
     __syncthreads();

@@ -50,7 +50,10 @@ constexpr int NLEV = LMAX - 1;    // levels 2 .. LMAX
 constexpr int BM = 128;           // chains per tile (TMEM lanes)
 constexpr int BK = 64;            // bytes (= int8 elements) of K per stage, one SWIZZLE_64B row
 constexpr int BN_DEFAULT = SB == 6 ? 64 : 80;  // Z columns per tile: NLEV x BN TMEM columns, 3 stages within 227 KB
-constexpr int STAGES = 3;
+#ifndef GTC_STAGES
+#define GTC_STAGES 3
+#endif
+constexpr int STAGES = GTC_STAGES;
 constexpr int A_SLOTS = SA;       // slot 0 doubles as the z slice for H tiles
 constexpr int A_TILE_BYTES = BM * BK;
 

@@ -116,7 +116,7 @@ __device__ __forceinline__ float f_cos(float x) { float r; asm("cos.approx.ftz.f
 __device__ __forceinline__ float f_exp(float x) { return f_ex2(x * 1.4426950408889634f); }
 
 struct PGTaskF {
-    float invK, p_right, rcp_left, mu, hz2;  // rcp_left = 1 / (1 - p_right)
+    float invK, p_right, z, hz2;
     bool small_z;
 };
 
@@ -127,12 +127,11 @@ __device__ __forceinline__ void pg1_setup_fast(float c, PGTaskF& s) {
     const float K = (float)(OCCU_PI * OCCU_PI / 8.0) + s.hz2;
     s.invK = f_rcp(K);
     s.small_z = z * t < 1.0f;
-    s.mu = f_rcp(fmaxf(z, 1.0f));  // only used when z t >= 1 (z >= 1.5625)
+    s.z = z;
     // q / p = (2K / pi) exp(K t) x { 4 Phi(-1.25)  |  2 exp(-z) }; overflow => p_right = 0
     const float qdivp = K * (s.small_z ? (float)(0.42259909466742100 * 2.0 / OCCU_PI) : (float)(4.0 / OCCU_PI)) *
                         f_exp(fmaf(K, t, s.small_z ? 0.0f : -z));
-    s.p_right = f_rcp(1.0f + qdivp);
-    s.rcp_left = f_rcp(1.0f - s.p_right);  // inf when p_right == 1 cannot happen: qdivp >= 0.33
+    s.p_right = f_rcp(1.0f + qdivp);  // 0 when qdivp overflows; never 1 (qdivp >= 0.33)
 }
 
 __device__ __forceinline__ bool pg1_round_fast(const PGTaskF& s, float ub, float ux, float u3, float us, float& x) {
@@ -156,14 +155,15 @@ __device__ __forceinline__ bool pg1_round_fast(const PGTaskF& s, float ub, float
             x = f_rcp(rx);
             pre = (x <= t) && (u3 <= f_exp(-s.hz2 * x));
         } else {
+            const float mu = f_rcp(s.z);  // z t >= 1 on this path
             const float cs = f_cos(6.283185307179586f * u3);
-            const float w = s.mu * (2.0f * L * cs * cs);  // mu Y^2, Y ~ N(0,1)
+            const float w = mu * (2.0f * L * cs * cs);  // mu Y^2, Y ~ N(0,1)
             const float disc = fmaf(0.25f * w, w, w);
             const float root = fmaf(disc, f_rsqrt(fmaxf(disc, 1e-30f)), fmaf(0.5f, w, 1.0f));  // 1 + w/2 + sqrt(w + w^2/4)
             // the two roots of Michael-Schucany-Haas are mu / root and mu root
-            const float ur = (ub - s.p_right) * s.rcp_left;
+            const float ur = (ub - s.p_right) * f_rcp(1.0f - s.p_right);
             const bool small_root = ur * (root + 1.0f) <= root;  // with probability mu / (mu + x), x = mu / root
-            x = small_root ? s.mu * f_rcp(root) : s.mu * root;
+            x = small_root ? mu * f_rcp(root) : mu * root;
             rx = f_rcp(x);
             pre = x <= t;
         }
