@@ -13,6 +13,22 @@
 // the same chains whatever the grid shape or the number of GPUs (reference contract: same
 // random_state => same chains, gibbs/tests/test_samplers.py:63-68).
 // ---------------------------------------------------------------------------------------------
+// The ten round keys (key + i * Weyl constants) depend on the seed only.  The host computes them once; kernels
+// that take them inside their parameter block use them as constant-bank operands, which removes the 18 key-update
+// instructions from every block (refill_rk below; same stream as refill()).
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+static inline void philox_round_keys(uint64_t seed, PhiloxKeys& rk) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; i++) {
+        rk.k[2 * i] = k0;
+        rk.k[2 * i + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
 struct Philox {
     uint32_t ctr[4];
     uint32_t key[2];
@@ -44,6 +60,25 @@ struct Philox {
             c3 = lo0;
             k0 += 0x9E3779B9u;
             k1 += 0xBB67AE85u;
+        }
+        buf[0] = c0;
+        buf[1] = c1;
+        buf[2] = c2;
+        buf[3] = c3;
+        ctr[3] += 1u;
+        have = 4;
+    }
+
+    __device__ __forceinline__ void refill_rk(const PhiloxKeys& rk) {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ rk.k[2 * i];
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ rk.k[2 * i + 1];
+            c3 = lo0;
         }
         buf[0] = c0;
         buf[1] = c1;
@@ -88,6 +123,16 @@ struct RT<float> {
     static __device__ __forceinline__ float erfc_(float x) { return erfcf(x); }
     static __device__ __forceinline__ float cospi_(float x) { return cospif(x); }
     static __device__ __forceinline__ float normcdfinv_(float x) { return normcdfinvf(x); }
+    // four uniforms from exactly one Philox block, round keys from the kernel parameters; (0, 1): the word is
+    // truncated to 24 significant bits (round toward zero) and centred by 2^-33
+    static __device__ __forceinline__ void unif4_rk(Philox& g, const PhiloxKeys& rk, float& a, float& b, float& c, float& d) {
+        g.refill_rk(rk);
+        g.have = 0;
+        a = fmaf(__uint2float_rz(g.buf[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        b = fmaf(__uint2float_rz(g.buf[1]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        c = fmaf(__uint2float_rz(g.buf[2]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        d = fmaf(__uint2float_rz(g.buf[3]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    }
     // four uniforms from exactly one Philox block
     static __device__ __forceinline__ void unif4(Philox& g, float& a, float& b, float& c, float& d) {
         g.refill();
@@ -107,6 +152,9 @@ struct RT<double> {
     static __device__ __forceinline__ double erfc_(double x) { return erfc(x); }
     static __device__ __forceinline__ double cospi_(double x) { return cospi(x); }
     static __device__ __forceinline__ double normcdfinv_(double x) { return normcdfinv(x); }
+    static __device__ __forceinline__ void unif4_rk(Philox& g, const PhiloxKeys&, double& a, double& b, double& c, double& d) {
+        unif4(g, a, b, c, d);
+    }
     // four 53-bit uniforms from two Philox blocks
     static __device__ __forceinline__ void unif4(Philox& g, double& a, double& b, double& c, double& d) {
         g.have = 0;

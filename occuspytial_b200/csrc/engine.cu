@@ -78,6 +78,7 @@ struct View {
     int model, n, p, r, q, pq, V, C, Cp, chain_offset;
     int n_pad, kq_pad, M, M_pad, ldz, ldh, ksplit, n_tiles, NV, bw;
     uint64_t seed;
+    PhiloxKeys rk;  // Philox round keys of the seed (constant-bank operands of the site pass)
     const double* W;
     const uint8_t* y;
     const int32_t* visit_ptr;
@@ -190,6 +191,7 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     v.Cp = round_up(P->chains, CHAIN_TILE);
     v.chain_offset = P->chain_offset;
     v.seed = P->seed;
+    philox_round_keys(P->seed, v.rk);
     v.n_pad = round_up(P->n, 128);
     v.kq_pad = round_up(v.pq, dgemm::BK);
     v.M = v.pq * (v.pq + 1) / 2;
@@ -421,7 +423,9 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
                 if (v.zprob) v.zprob[off] = pr;
                 Philox g;
                 g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
-                zc = g.unif_d() < pr ? 1 : 0;  // logit.py:246 / 250
+                g.refill_rk(v.rk);
+                const uint64_t bits = ((uint64_t)g.buf[0] << 21) ^ (uint64_t)(g.buf[1] >> 11);  // == g.unif_d()
+                zc = ((double)bits + 0.5) * (1.0 / 9007199254740992.0) < pr ? 1 : 0;  // logit.py:246 / 250
             }
             v.z[off] = (uint8_t)zc;
             if (!SLICES) v.kd[off] = (double)zc - 0.5;  // logit.py:252
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View 
         }
         if (have) {
             PGT ub, ux, u3, us, x;
-            RT<PGT>::unif4(g, ub, ux, u3, us);
+            RT<PGT>::unif4_rk(g, v.rk, ub, ux, u3, us);
             if (PGSel<PGT>::round(task, ub, ux, u3, us, x)) {
                 have = false;
                 const double om = 0.25 * (double)x;
