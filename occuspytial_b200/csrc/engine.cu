@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <type_traits>
@@ -374,8 +375,11 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 //  SLICES (tcgen05 Gram path): phase 3 writes omega as SA base-256 digits of its 48-bit fixed-point value and z as one
 //          more byte plane, site-contiguous per chain (gram_tc.cuh: Aq[s][chain][site]) -- the A operand of the Gram
 //          kernel, 7 bytes per site instead of the two FP64 arrays omega and kd; a debug engine also writes omega.
+#ifndef SITE_MIN_BLOCKS
+#define SITE_MIN_BLOCKS 1
+#endif
 template <int R, typename PGT, bool SLICES>
-__global__ void __launch_bounds__(CHAIN_TILE) site_pass_logit_kernel(const View v) {
+__global__ void __launch_bounds__(CHAIN_TILE, SITE_MIN_BLOCKS) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     extern __shared__ __align__(16) unsigned char site_smem[];
     PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // column tid is private to thread tid
@@ -869,7 +873,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
                                                                          double* rec_alpha, double* rec_beta,
                                                                          double* rec_tau, int rec_capacity) {
     extern __shared__ double sm_dyn[];
-    const int c = blockIdx.x, tid = threadIdx.x, T = SOLVE_THREADS;
+    const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;  // 64 (q <= 128) or SOLVE_THREADS
     double* sm = v.solve_stride ? v.solve_scratch + (size_t)c * v.solve_stride : sm_dyn;
     const int p = v.p, q = v.q, r = v.r, pq = v.pq;
     const int qb = (q + 3) / 4, q4 = qb * 4;
@@ -2302,6 +2306,18 @@ static size_t icar_smem_bytes(const View& v) {
 
 static size_t solve_smem_bytes(const View& v) { return solve_bytes_for(v.q, v.p, v.pq); }
 
+// Threads per chain in the RSR solve.  Most phases of the blocked factorisation keep only a few dozen threads busy
+// and the kernel is barrier bound: for small q fewer threads per chain put more chains on an SM.
+static int solve_threads_for(int q) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* s = getenv("OCCU_SOLVE_THREADS");
+        forced = s ? atoi(s) : 0;
+    }
+    if (forced >= 32 && forced <= SOLVE_THREADS && forced % 32 == 0 && (q + 3) / 4 <= forced) return forced;
+    return SOLVE_THREADS;
+}
+
 #define PROF_MARK(e, k, st)                                           \
     do {                                                              \
         if ((e)->profiling) cudaEventRecord((e)->ev[k], st);          \
@@ -2356,7 +2372,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    solve_logit_rsr_kernel<<<v.Cp, SOLVE_THREADS, smem, st>>>(v, dbg, ra, rb, rt, cap);
+    solve_logit_rsr_kernel<<<v.Cp, solve_threads_for(v.q), smem, st>>>(v, dbg, ra, rb, rt, cap);
     e->launches++;
     PROF_MARK(e, KC_COUNT, st);
     CUDA_OK(cudaGetLastError());
