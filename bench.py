@@ -187,6 +187,9 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION prints a banner on stdout, which must carry exactly one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from occuspytial_b200 import LogitRSRGibbs, _lib
     from occuspytial_b200.gibbs.parallel import allgather_summaries
