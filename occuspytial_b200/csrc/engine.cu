@@ -2269,6 +2269,9 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     p.Cp = v.Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
     p.n_gt = g.n_gt; p.n_ht = g.n_ht; p.Mrows = g.Mrows; p.M = v.M; p.pq = v.pq; p.ldg = v.M_pad; p.ldh = v.ldh;
     p.scale = v.tscale; p.hshift = v.hshift; p.err = v.tc_err; p.mode = 0;
+    // measured (B200): with several K chunks and omega planes larger than the Z slices, column-tile-fastest order is
+    // 13 % faster (n = 50k, 4096 chains); with one chunk chain-tile-fastest wins by 2-20 %
+    p.nt_fastest = g.nsplit > 1 && (size_t)(gtc::SA + 1) * v.Cp > (size_t)gtc::SB * g.Mrows;
     p.Gpart = g.nsplit > 1 ? v.Gp : v.G;
     p.Hpart = g.nsplit > 1 ? v.Hp : v.Hpart;
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;

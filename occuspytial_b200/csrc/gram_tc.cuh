@@ -97,6 +97,7 @@ struct Params {
     double* Gpart;         // [nsplit][Cp][ldg]
     double* Hpart;         // [nsplit][Cp][ldh]
     int* err;              // set to 1 if a barrier wait times out (debug aid; 0 otherwise)
+    int nt_fastest;        // item order inside a K chunk (decode_item)
     int mode;              // 0 = normal; bottleneck probes (results are garbage): 1 = no TMA loads, 2 = no MMAs
 };
 
@@ -288,14 +289,22 @@ struct Item {
     bool is_h;
 };
 __device__ __forceinline__ Item decode_item(const Params& p, int item) {
-    // G items first (all chain tiles of one column tile are adjacent so that a wave shares few Z tiles), the
-    // four-times cheaper H items last: they back-fill the tail of the last wave.
+    // Item order = which operand tiles the ~148 concurrently running CTAs share through L2.  K chunks are outermost
+    // (all CTAs of a wave walk the same K range); inside a chunk the column tile runs fastest when the omega/z
+    // planes are the larger operand (each chain tile is then streamed from HBM once and the Z slices are re-read
+    // per group of chain tiles), the chain tile runs fastest otherwise.
     Item it;
-    const int per_tile = p.nsplit;
-    const int tile = item / per_tile;
-    it.chunk = item - tile * per_tile;
-    it.mt = tile % p.MT;
-    it.nt = tile / p.MT;
+    const int NT = p.n_gt + p.n_ht;
+    const int tiles = p.MT * NT;
+    it.chunk = item / tiles;
+    const int rem = item - it.chunk * tiles;
+    if (p.nt_fastest) {
+        it.mt = rem / NT;
+        it.nt = rem - it.mt * NT;
+    } else {
+        it.nt = rem / p.MT;
+        it.mt = rem - it.nt * p.MT;
+    }
     it.is_h = it.nt >= p.n_gt;
     it.kb0 = it.chunk * p.kb_per_chunk;
     it.kb1 = min(it.kb0 + p.kb_per_chunk, p.kblocks);
