@@ -66,3 +66,58 @@ def test_full_size_sharding_and_determinism(big):
     for k in ('alpha', 'beta', 'tau'):
         np.testing.assert_array_equal(out[0][k][128:], out[1][k])
         np.testing.assert_array_equal(out[0][k], out[2][k])
+
+
+@pytest.mark.parametrize('shape,q,chains', [((100, 100), 64, 3),     # headline shape: one K chunk, G written directly
+                                             ((100, 120), 12, 5)])    # n = 12000: two K chunks + fixed-order reduction
+def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains):
+    """The Omega-weighted Gram of the tcgen05 kind::i8 path (csrc/gram_tc.cuh) at sizes the small parity cases do
+    not reach: every Gaussian system built from it agrees with a NumPy FP64 evaluation to 1e-10
+    (reference: logit.py:226-232, 325-337, 478-485)."""
+    from occuspytial_b200 import LogitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.gibbs import _setup
+    from oracle import sweep as S
+    n = shape[0] * shape[1]
+    Q, W, X, y, *_ = make_data(n=n, min_v=2, max_v=6, lattice=shape, random_state=1)
+    K = _setup.rsr_basis(Q, X, q=q)
+    s = LogitRSRGibbs(Q, W, X, y, random_state=4, K=K)
+    f = s.fixed
+    prob = s._problem_arrays()
+    V, r, p = prob['W_rows'].shape[0], 3, 3
+    rng = np.random.default_rng(8)
+    eng = s._make_engine(chains, seed=3, debug=True)     # n >= 1024: the tcgen05 path is the default
+    assert eng.gram_int8
+    st = dict(alpha=rng.normal(size=(chains, r)), beta=rng.normal(size=(chains, p)), tau=rng.uniform(0.3, 3, chains),
+              eta=rng.normal(size=(chains, q)))
+    eng.set_start(st)
+    eng.debug_site_half()                                # z and omega_b drawn on the device, written as byte planes
+    z = eng.get_field(_lib.F_Z).astype(float)
+    omega = eng.get_field(_lib.F_OMEGA)
+    assert np.all(omega > 0) and np.all(np.isfinite(omega))
+    normals = rng.normal(size=(chains, q + p + r))
+    omega_a = rng.uniform(0.02, 0.25, size=(chains, V))
+    out = eng.debug_gaussian_half(normals=normals, tau=st['tau'], omega_a=omega_a)
+    assert out['fails'] == 0
+    eta_new = eng.get_field(_lib.F_ETA)
+    for c in range(chains):
+        k = z[c] - 0.5
+        Lam, b = S.eta_rsr_system(f.K, X, omega[c], k, st['beta'][c], st['tau'][c], f.Q)
+        scale = np.abs(Lam).max()
+        np.testing.assert_allclose(out['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * scale)
+        np.testing.assert_allclose(out['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+        A, bb = S.beta_system_logit(X, omega[c], k, f.K @ eta_new[c], f.b_prec, f.b_prec_by_mu)
+        np.testing.assert_allclose(out['beta_prec'][c], A, rtol=1e-10, atol=1e-12 * np.abs(A).max())
+        np.testing.assert_allclose(out['beta_b'][c], bb, rtol=1e-9, atol=1e-10 * np.abs(bb).max())
+    # injected omega / z (set_field) go through the slicing kernel instead of the site pass: same systems
+    om2 = rng.uniform(0.01, 0.4, size=omega.shape)
+    z2 = (rng.random(z.shape) < 0.5).astype(np.uint8)
+    eng.set_start(st)
+    eng.set_field(_lib.F_OMEGA, om2)
+    eng.set_field(_lib.F_Z, z2)
+    out2 = eng.debug_gaussian_half(normals=normals, tau=st['tau'], omega_a=omega_a)
+    for c in range(chains):
+        Lam, b = S.eta_rsr_system(f.K, X, om2[c], z2[c] - 0.5, st['beta'][c], st['tau'][c], f.Q)
+        np.testing.assert_allclose(out2['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
+        np.testing.assert_allclose(out2['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+    eng.close()
