@@ -375,23 +375,23 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 //  SLICES (tcgen05 Gram path): phase 3 writes omega as SA base-256 digits of its 48-bit fixed-point value and z as one
 //          more byte plane, site-contiguous per chain (gram_tc.cuh: Aq[s][chain][site]) -- the A operand of the Gram
 //          kernel, 7 bytes per site instead of the two FP64 arrays omega and kd; a debug engine also writes omega.
-#ifndef SITE_MIN_BLOCKS
-#define SITE_MIN_BLOCKS 1
-#endif
+// resident CTAs per SM the register allocation aims at: 8 (64 registers) for the usual r <= 4, fewer when the
+// r (r + 1) / 2 + r FP64 accumulators no longer fit
+constexpr int site_min_blocks(int r) { return r <= 4 ? 8 : (r <= 6 ? 5 : 3); }
 template <int R, typename PGT, bool SLICES>
-__global__ void __launch_bounds__(CHAIN_TILE, SITE_MIN_BLOCKS) site_pass_logit_kernel(const View v) {
+__global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     extern __shared__ __align__(16) unsigned char site_smem[];
     PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // column tid is private to thread tid
     const int tid = threadIdx.x;
-    const int c = blockIdx.y * CHAIN_TILE + tid;
-    const int tile = blockIdx.x;
-    const int i0 = tile * SITE_TILE;
-    const int i1 = min(i0 + SITE_TILE, v.n);
     const uint32_t iter = v.ctl->iter;
     const bool first = v.ctl->first != 0;
-    const uint32_t gc = (uint32_t)(v.chain_offset + c);
     const size_t Cp = v.Cp;
+    const int tile = blockIdx.x;
+    const int c = blockIdx.y * CHAIN_TILE + tid;
+    const int i0 = tile * SITE_TILE;
+    const int i1 = min(i0 + SITE_TILE, v.n);
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
 
     double al[R];
 #pragma unroll

@@ -312,7 +312,10 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+#ifndef GTC_MIN_BLOCKS
+#define GTC_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(THREADS, GTC_MIN_BLOCKS)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
