@@ -160,7 +160,7 @@ int run(int n, int C, int pq, int want_split) {
     p.Cp = Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
     p.n_gt = g.n_gt; p.n_ht = g.n_ht; p.Mrows = g.Mrows; p.M = M; p.pq = pq; p.ldg = M64; p.ldh = pq64;
     p.scale = scale; p.Gpart = Gpart; p.Hpart = Hpart; p.err = err; p.mode = 0; p.hshift = nullptr;
-    p.nt_fastest = getenv("NT_FASTEST") ? atoi(getenv("NT_FASTEST")) : (g.nsplit > 1 && (size_t)(gtc::SA + 1) * Cp > (size_t)gtc::SB * g.Mrows);
+    p.order = getenv("TC_ORDER") ? atoi(getenv("TC_ORDER")) : 0;
 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));

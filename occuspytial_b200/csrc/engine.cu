@@ -138,6 +138,7 @@ struct occu_engine {
     size_t ws_bytes;
     gtc::Geometry geo;
     int sm_count;
+    int tc_order;           // tile order of the tcgen05 Gram (gtc::Params::order; OCCU_TC_ORDER overrides)
     CUtensorMap tmA, tmB;
     bool slices_valid;      // Aq holds the digits of the current (omega, z)
     bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines)
@@ -2269,9 +2270,7 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     p.Cp = v.Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
     p.n_gt = g.n_gt; p.n_ht = g.n_ht; p.Mrows = g.Mrows; p.M = v.M; p.pq = v.pq; p.ldg = v.M_pad; p.ldh = v.ldh;
     p.scale = v.tscale; p.hshift = v.hshift; p.err = v.tc_err; p.mode = 0;
-    // measured (B200): with several K chunks and omega planes larger than the Z slices, column-tile-fastest order is
-    // 13 % faster (n = 50k, 4096 chains); with one chunk chain-tile-fastest wins by 2-20 %
-    p.nt_fastest = g.nsplit > 1 && (size_t)(gtc::SA + 1) * v.Cp > (size_t)gtc::SB * g.Mrows;
+    p.order = e->tc_order;
     p.Gpart = g.nsplit > 1 ? v.Gp : v.G;
     p.Hpart = g.nsplit > 1 ? v.Hp : v.Hpart;
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
@@ -2427,6 +2426,8 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         int dev = 0;
         e->sm_count = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+        const char* ord = getenv("OCCU_TC_ORDER");
+        e->tc_order = ord ? atoi(ord) : 0;
     }
     for (int k = 0; k < KC_COUNT; k++) { e->kernel_ms[k] = 0.0; e->kernel_calls[k] = 0; }
     for (int k = 0; k <= KC_COUNT; k++) e->ev[k] = nullptr;

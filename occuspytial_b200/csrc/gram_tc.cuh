@@ -97,7 +97,7 @@ struct Params {
     double* Gpart;         // [nsplit][Cp][ldg]
     double* Hpart;         // [nsplit][Cp][ldh]
     int* err;              // set to 1 if a barrier wait times out (debug aid; 0 otherwise)
-    int nt_fastest;        // item order inside a K chunk (decode_item)
+    int order;             // item order inside a K chunk (Sched::decode_g): 0 super-tiles, 1 column tile fastest, 2 chain tile fastest
     int mode;              // 0 = normal; bottleneck probes (results are garbage): 1 = no TMA loads, 2 = no MMAs
 };
 
@@ -288,28 +288,93 @@ struct Item {
     int mt, nt, kb0, kb1, chunk;
     bool is_h;
 };
-__device__ __forceinline__ Item decode_item(const Params& p, int item) {
-    // Item order = which operand tiles the ~148 concurrently running CTAs share through L2.  K chunks are outermost
-    // (all CTAs of a wave walk the same K range); inside a chunk the column tile runs fastest when the omega/z
-    // planes are the larger operand (each chain tile is then streamed from HBM once and the Z slices are re-read
-    // per group of chain tiles), the chain tile runs fastest otherwise.
-    Item it;
-    const int NT = p.n_gt + p.n_ht;
-    const int tiles = p.MT * NT;
-    it.chunk = item / tiles;
-    const int rem = item - it.chunk * tiles;
-    if (p.nt_fastest) {
-        it.mt = rem / NT;
-        it.nt = rem - it.mt * NT;
-    } else {
-        it.nt = rem / p.MT;
-        it.mt = rem - it.nt * p.MT;
+// Static work schedule of one persistent CTA; the three warp roles walk the same sequence independently.
+//  * Gram items (tile, K chunk) round-robin over the CTAs.  Their order decides which operand tiles the ~148
+//    concurrently running CTAs share through L2: K chunks are outermost (a wave walks one K range); inside a chunk
+//    the order is p.order (decode_g).
+//  * The U'z items cost 6/21 of a Gram item.  They go first to the CTAs that received one Gram item less (up to
+//    three each), so that they fill the tail of the last wave instead of extending it (n = 10^4, 4096 chains:
+//    1152 Gram items on 148 CTAs = 116 x 8 + 32 x 7; the 64 cheap items make it 32 x (7 + 2), makespan 8 not 8.3).
+struct Sched {
+    int b, grid, nG, nH, roundsG, r, L, hq, k;
+    __device__ __forceinline__ Sched(const Params& p) {
+        b = blockIdx.x;
+        grid = gridDim.x;
+        nG = p.MT * p.n_gt * p.nsplit;
+        nH = p.MT * p.n_ht * p.nsplit;
+        roundsG = (nG + grid - 1) / grid;
+        r = nG % grid;                       // CTAs [0, r) hold one Gram item more (r == 0: all equal)
+        L = r == 0 ? grid : grid - r;        // light CTAs
+        hq = min((nH + L - 1) / L, 3);       // cheap items each light CTA takes before the rest is shared
+        k = 0;
     }
-    it.is_h = it.nt >= p.n_gt;
-    it.kb0 = it.chunk * p.kb_per_chunk;
-    it.kb1 = min(it.kb0 + p.kb_per_chunk, p.kblocks);
-    return it;
-}
+    __device__ __forceinline__ void decode_g(const Params& p, int idx, Item& it) const {
+        const int tiles = p.MT * p.n_gt;
+        it.chunk = idx / tiles;
+        const int rem = idx - it.chunk * tiles;
+        it.is_h = false;
+        if (p.order == 1) {          // column tile fastest
+            it.mt = rem / p.n_gt;
+            it.nt = rem - it.mt * p.n_gt;
+        } else if (p.order == 2) {   // chain tile fastest
+            it.nt = rem / p.MT;
+            it.mt = rem - it.nt * p.MT;
+        } else {
+            // super-tiles of GM chain tiles x GN column tiles (~ one wave of CTAs), chain tile fastest inside, super-tile
+            // columns fastest outside: the HBM traffic  A NT / GN + B MT / GM  under GM GN = 148 is minimal at
+            // GM = sqrt(0.43 x 148) ~ 8 whatever the problem size (A: 7 x 128 bytes per chain-tile row of K, B: 6 x 64)
+            constexpr int GM = 8, GN = 19;
+            const int per_brow = GM * p.n_gt;
+            const int bm = rem / per_brow;
+            const int rem2 = rem - bm * per_brow;
+            const int hm = min(GM, p.MT - bm * GM);
+            const int bn = rem2 / (hm * GN);
+            const int rem3 = rem2 - bn * hm * GN;
+            const int ntl = rem3 / hm;
+            it.mt = bm * GM + (rem3 - ntl * hm);
+            it.nt = bn * GN + ntl;
+        }
+    }
+    __device__ __forceinline__ void decode_h(const Params& p, int h, Item& it) const {
+        const int tiles = p.MT * p.n_ht;
+        it.chunk = h / tiles;
+        const int rem = h - it.chunk * tiles;
+        const int j = rem / p.MT;
+        it.mt = rem - j * p.MT;
+        it.nt = p.n_gt + j;
+        it.is_h = true;
+    }
+    __device__ __forceinline__ bool next(const Params& p, Item& it) {
+        for (;;) {
+            bool found = false;
+            if (k < roundsG) {
+                const int idx = b + k * grid;
+                if (idx < nG) {
+                    decode_g(p, idx, it);
+                    found = true;
+                }
+            } else if (k < roundsG + hq) {
+                const int rho = r == 0 ? b : b - r;
+                const int h = rho + (k - roundsG) * L;
+                if (rho >= 0 && h < nH) {
+                    decode_h(p, h, it);
+                    found = true;
+                }
+            } else {
+                const int h = hq * L + b + (k - roundsG - hq) * grid;
+                if (h >= nH) return false;
+                decode_h(p, h, it);
+                found = true;
+            }
+            k++;
+            if (found) {
+                it.kb0 = it.chunk * p.kb_per_chunk;
+                it.kb1 = min(it.kb0 + p.kb_per_chunk, p.kblocks);
+                return true;
+            }
+        }
+    }
+};
 
 template <int BN>
 #ifndef GTC_MIN_BLOCKS
@@ -328,7 +393,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nitems = p.MT * (p.n_gt + p.n_ht) * p.nsplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -355,8 +419,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            Sched sched(p);
+            Item it;
+            while (sched.next(p, it)) {
                 const int arow = it.mt * BM;
                 const int brow = it.nt * BN;
                 const uint32_t bytes = (it.is_h ? A_TILE_BYTES : SA * A_TILE_BYTES) + SB * C::B_TILE_BYTES;
@@ -398,8 +463,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            Sched sched(p);
+            Item it;
+            while (sched.next(p, it)) {
                 mbar_wait(tmem_empty, acc_phase ^ 1, p.err);  // epilogue has drained the accumulators
                 tc_fence_after();
                 for (int kb = it.kb0; kb < it.kb1; kb++) {
@@ -429,8 +495,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue =====================
         const int quarter = warp & 3;  // TMEM lanes [32 quarter, 32 quarter + 32) are the ones this warp may read
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const Item it = decode_item(p, item);
+        Sched sched(p);
+        Item it;
+        while (sched.next(p, it)) {
             mbar_wait(tmem_full, acc_phase, p.err);
             tc_fence_after();
             const int c = it.mt * BM + quarter * 32 + lane;
