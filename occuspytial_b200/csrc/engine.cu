@@ -826,13 +826,26 @@ __global__ void __launch_bounds__(32) alpha_tau_kernel(const View v, const Solve
 }
 
 // asum[k][c] = sum_tile apart[tile][k][c], fixed order
-__global__ void reduce_partials_kernel(const View v) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Block = 32 sums x 8 interleaved slices of the site tiles (8 x the loads in flight of a one-thread-per-sum loop),
+// combined in slice order: the summation order is fixed, so the result is reproducible.
+constexpr int RED_SPLIT = 8;
+__global__ void __launch_bounds__(32 * RED_SPLIT) reduce_partials_kernel(const View v) {
+    __shared__ double part[RED_SPLIT][33];
+    const size_t idx = (size_t)blockIdx.x * 32 + threadIdx.x;
     const size_t per = (size_t)v.NV * v.Cp;
-    if (idx >= per) return;
     double s = 0.0;
-    for (int t = 0; t < v.n_tiles; t++) s += v.apart[(size_t)t * per + idx];
-    v.asum[idx] = s;
+    if (idx < per) {
+#pragma unroll 4
+        for (int t = threadIdx.y; t < v.n_tiles; t += RED_SPLIT) s += v.apart[(size_t)t * per + idx];
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && idx < per) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < RED_SPLIT; k++) tot += part[k][threadIdx.x];
+        v.asum[idx] = tot;
+    }
 }
 
 // ---- 4x4-blocked Cholesky machinery of the RSR solve ------------------------------------------------
@@ -2345,7 +2358,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     if (v.model != OCCU_LOGIT_ICAR && launch_gram_gemm(e, st)) return -1;
     PROF_MARK(e, KC_REDUCE, st);
     const size_t per = (size_t)v.NV * v.Cp;
-    reduce_partials_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(v);
+    reduce_partials_kernel<<<(unsigned)((per + 31) / 32), dim3(32, RED_SPLIT), 0, st>>>(v);
     alpha_tau_kernel<<<(v.Cp + 31) / 32, 32, 0, st>>>(v, dbg, ra, cap);  // 1 warp per CTA: spread over all SMs
     e->launches += 2;
     PROF_MARK(e, KC_SOLVE, st);
