@@ -67,3 +67,37 @@ class Chain:
 
     def __repr__(self):
         return f'Chain(params: {self._names}, size: {self._index})'
+
+
+class ChainViews:
+    """Read-only sequence of the per-chain :class:`Chain` objects of a lock-step run.
+
+    The engine returns all chains stacked, ``{name: (chains, draws[, dim])}``; the reference's API is a list of
+    ``Chain`` objects (parallel.py:38-42).  Building thousands of views eagerly costs milliseconds per ``sample``
+    call, so a view is made (zero-copy) when a chain is first asked for.
+    """
+
+    def __init__(self, stacked):
+        self._stacked = stacked
+        self._n = int(next(iter(stacked.values())).shape[0])
+        self._cache = {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError('chain index out of range')
+        if i not in self._cache:
+            self._cache[i] = Chain.from_arrays({k: v[i] for k, v in self._stacked.items()})
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def __repr__(self):
+        return f'ChainViews({self._n} chains)'

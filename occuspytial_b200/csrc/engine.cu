@@ -1191,12 +1191,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
 // stand-alone primitives
 // ------------------------------------------------------------------------------------------------
 template <typename PGT>
-__global__ void pg1_kernel(const double* __restrict__ c, size_t count, uint64_t seed, double* __restrict__ out) {
+__global__ void pg1_kernel(const double* __restrict__ c, size_t count, uint64_t seed, const PhiloxKeys rk,
+                           double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Philox g;
     g.init(seed, (uint32_t)(i >> 32), (uint32_t)i, 0u, ST_HOOK);
-    out[i] = (double)pg1_draw<PGT>((PGT)c[i], g);
+    out[i] = (double)pg1_draw<PGT>((PGT)c[i], g, rk);
 }
 
 __global__ void truncnorm_kernel(const double* __restrict__ loc, const uint8_t* __restrict__ positive,
@@ -2748,8 +2749,10 @@ int occu_pg1(const double* c, size_t count, uint64_t seed, int fp64, double* out
     if (!count) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((count + 255) / 256);
-    if (fp64) pg1_kernel<double><<<blocks, 256, 0, st>>>(c, count, seed, out);
-    else pg1_kernel<float><<<blocks, 256, 0, st>>>(c, count, seed, out);
+    PhiloxKeys rk;
+    philox_round_keys(seed, rk);
+    if (fp64) pg1_kernel<double><<<blocks, 256, 0, st>>>(c, count, seed, rk, out);
+    else pg1_kernel<float><<<blocks, 256, 0, st>>>(c, count, seed, rk, out);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -205,14 +205,16 @@ struct PGSel<float> {
     }
 };
 
+// One PG(1, c) variate: the production loop of the site pass (setup once, one Philox block per rejection round,
+// round keys from the kernel parameters) as a stand-alone function for the test hook occu_pg1.
 template <typename T>
-__device__ __forceinline__ T pg1_draw(T c, Philox& g) {
+__device__ __forceinline__ T pg1_draw(T c, Philox& g, const PhiloxKeys& rk) {
     typedef RT<T> R;
     typename PGSel<T>::Task s;
     PGSel<T>::setup(c, s);
     for (;;) {
         T ub, ux, u3, us, x;
-        R::unif4(g, ub, ux, u3, us);
+        R::unif4_rk(g, rk, ub, ux, u3, us);
         if (PGSel<T>::round(s, ub, ux, u3, us, x)) return (T)0.25 * x;
     }
 }

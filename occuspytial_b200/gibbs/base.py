@@ -10,7 +10,7 @@ import numpy as np
 from scipy.sparse import csc_matrix, isspmatrix_csc
 from tqdm.auto import tqdm
 
-from ..chain import Chain
+from ..chain import Chain, ChainViews
 from ..data import Data
 from ..posterior import PosteriorParameter
 from ..state import State, FixedState
@@ -180,11 +180,11 @@ class GibbsBase:
                     a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
 
     def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=None):
-        """Engine for ``chains`` chains.  ``gram_int8``: True / False force the Gram path of LogitRSR (exact INT8
-        slice GEMMs / hand-written FP64 DMMA kernel); None picks INT8 when the problem is large enough for the
-        tensor-core path to pay (>= 1024 sites; the rule must not depend on the number of chains, or a shard of a
-        job would round differently from the whole job) and falls back to the DMMA kernel -- another GPU kernel
-        of this engine, not a CPU path -- if cuBLASLt offers no INT8 algorithm for the shape."""
+        """Engine for ``chains`` chains.  ``gram_int8``: True / False force the Gram path of LogitRSR (exact integer
+        slicing on the tcgen05 tensor cores / hand-written FP64 DMMA kernel); None picks the tcgen05 path when the
+        problem is large enough for it to pay (>= 1024 sites; the rule must not depend on the number of chains, or a
+        shard of a job would round differently from the whole job) and falls back to the DMMA kernel -- another GPU
+        kernel of this engine, not a CPU path -- if the TMA descriptors cannot be encoded."""
         from ..engine import DeviceEngine
         from .._lib import EngineError
         if self._model is None:
@@ -192,7 +192,10 @@ class GibbsBase:
         auto = gram_int8 is None
         if auto:
             gram_int8 = self._model == 'logit_rsr' and self.fixed.n >= 1024
-        problem = self._problem_arrays()
+        problem = self.__dict__.get('_problem_cache')
+        if problem is None:   # flattening the ragged W / y dictionaries is the costly part: once per sampler
+            problem = self._problem_arrays()
+            self.__dict__['_problem_cache'] = problem
         try:
             return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
                                 device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8)
@@ -260,7 +263,9 @@ class GibbsBase:
             per_draw = 8 * local * sum(dims.values())
             capacity = int(max(1, min(draws, _RECORD_BYTES // per_draw)))
             record = engine.alloc_record(capacity)
-            host = {k: np.empty((local, draws) + ((d,) if d > 1 else ())) for k, d in dims.items()}
+            shapes = {k: (local, draws) + ((d,) if d > 1 else ()) for k, d in dims.items()}
+            # one record block holds every draw (the usual case): its host copy is the result, no staging array
+            host = {k: (None if capacity >= draws else np.empty(shp)) for k, shp in shapes.items()}
             block = int(min(max(1, size // 20), 256))
             bar = tqdm(total=size, disable=not progressbar, position=pos)
             done, filled, flushed = 0, 0, 0
@@ -272,7 +277,10 @@ class GibbsBase:
                 for k, d in dims.items():
                     part = record[k][:, :filled].cpu().numpy()
                     engine.d2h_bytes += part.nbytes
-                    host[k][:, flushed:flushed + filled] = part.reshape(host[k][:, flushed:flushed + filled].shape)
+                    if host[k] is None:   # everything fitted in one block: the copy IS the result
+                        host[k] = part.reshape(shapes[k])
+                    else:
+                        host[k][:, flushed:flushed + filled] = part.reshape(host[k][:, flushed:flushed + filled].shape)
                 flushed += filled
                 filled = 0
 
@@ -299,7 +307,7 @@ class GibbsBase:
                                     d2h_bytes=engine.d2h_bytes, chains=local, chain_offset=lo)
         finally:
             engine.close()
-        out = [Chain.from_arrays({k: host[k][c] for k in dims}) for c in range(local)]
+        out = ChainViews(host)
         self.chain = out[0]
         self._last_arrays = host
         return out
