@@ -309,12 +309,12 @@ def run_b200(args):
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     total_ms = sum(v[0] / max(v[1], 1) for v in kms.values())
     if gram_path == 'int8':
-        # executed INT8 operations of gram_tc_kernel (csrc/gram_tc.cuh): 21 slice pairs (6 omega x 6 Z slices, levels
-        # s + t <= 7) over 128-chain x 64-column tiles, plus the 6 slices of the U'z tiles
-        BN, PAIRS, SB = 64, 21, 6
-        Kp = -(-wl['n'] // 64) * 64
-        Cp = -(-args.chains // 128) * 128
-        int8_ops = 2.0 * Cp * Kp * BN * (-(-M // BN) * PAIRS + -(-pq // BN) * SB)
+        # gram_tc_kernel (csrc/gram_tc.cuh): 21 slice pairs (6 omega x 6 Z slices, levels s + t <= 7) over 128-chain x
+        # 64-column tiles, plus the 6 slices of the U'z tiles
+        PAIRS, SB = 21, 6
+        # useful INT8 operations of the slicing algorithm (no tile / K padding counted): PAIRS products of the
+        # [chains x n] omega planes with the [n x M] Z planes, SB products of the z plane with the [n x pq] U planes
+        int8_ops = 2.0 * args.chains * wl['n'] * (M * PAIRS + pq * SB)
         int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
         traffic = None
         try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
@@ -352,6 +352,20 @@ def run_b200(args):
                                'note': 'the site pass is instruction-issue bound (PG sampling), not HBM bound',
                                'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'},
     }
+    # whole-step ceilings of SURVEY.md 8(d): F_alg / P64 (the reference's FP64 arithmetic on the FP64 pipe) and
+    # B_alg / BW (every per-chain vector crossing HBM once per stage); the tcgen05 Gram leaves the first behind
+    r_ = 3
+    f_alg = wl['n'] * pq * (pq + 1) + 4 * wl['n'] * pq + (wl['q'] ** 3 + wl['p'] ** 3 + r_ ** 3) / 3 \
+        + 4 * (wl['q'] ** 2 + wl['p'] ** 2 + r_ ** 2) + 0.5 * wl['V'] * r_ * (r_ + 1) + 4 * wl['V'] * r_
+    b_alg = 35 * wl['n'] + 16 * pq ** 2
+    per_gpu = value / world
+    line['step_roofline'] = {
+        'alg_flops_per_chain_iteration': f_alg, 'alg_bytes_per_chain_iteration': b_alg,
+        'fp64_pipe_ceiling_chain_it_per_s': peak64 * 1e12 / f_alg, 'hbm_ceiling_chain_it_per_s': hbm_peak * 1e9 / b_alg,
+        'value_over_fp64_pipe_ceiling': per_gpu / (peak64 * 1e12 / f_alg),
+        'value_over_hbm_ceiling': per_gpu / (hbm_peak * 1e9 / b_alg),
+        'note': 'per GPU; the FP64-pipe ceiling is what bounds an FP64 implementation of the sweep (cuBLAS DGEMM rate); '
+                'the Gram runs as exact integer slices on the INT8 tensor pipe instead, so the step exceeds it'}
     if dmma_info:
         tf = gram_flops_alg / (dmma_info['ms_per_launch'] * 1e-3) / 1e12
         dmma_info.update({'bound': 'tensor', 'achieved': tf, 'peak': peak64, 'unit': 'TFLOP/s', 'frac': tf / peak64,
