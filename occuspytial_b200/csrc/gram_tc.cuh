@@ -148,28 +148,9 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// K-major SWIZZLE_64B operand tile: rows of 64 bytes, 8-row groups 512 bytes apart (canonical layout
-// ((8,n),2):((4,SBO),1) in 16-byte units), descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);        // start address
-    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(512 >> 4) << 32;              // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                       // version
-    d |= (uint64_t)4 << 61;                       // SWIZZLE_64B
-    return d;
-}
 // kind::i8 instruction descriptor: D = S32, A = u8 (K-major), B = s8 (K-major), M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_i8(int n) {
     return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
     asm volatile(
@@ -180,7 +161,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Low word of a SWIZZLE_64B K-major descriptor; byte offsets inside a stage are added as (bytes >> 4).
+// Shared-memory matrix descriptor of a K-major SWIZZLE_64B operand tile: rows of 64 bytes, 8-row groups 512 bytes
+// apart (canonical layout ((8,n),2):((4,SBO),1) in 16-byte units), descriptor version 1 (sm_100).  Low word = start
+// address >> 4 | leading byte offset (unused for swizzled K-major, set to 1); byte offsets inside a stage are added
+// to it as (bytes >> 4).
 __device__ __forceinline__ uint32_t desc_lo_sw64(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
 constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO = 512 B, version 1, SWIZZLE_64B
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo) { return ((uint64_t)DESC_HI_SW64 << 32) | lo; }
