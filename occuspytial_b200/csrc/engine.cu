@@ -172,6 +172,10 @@ static size_t solve_bytes_for(int q, int p, int pq) {
     return doubles * sizeof(double) + 2 * nblk + 16;
 }
 
+// scratch / shared-memory sizes of the tiled large-q solve (solve_logit_rsr_tiled_kernel)
+static size_t tiled_scratch_doubles(int q, int p);
+static size_t tiled_smem_bytes(int q);
+
 static int fill_dims(const occu_problem_t* P, View& v) {
     if (!P) return set_err("null problem");
     if (P->abi_version != OCCU_ABI_VERSION) return set_err("ABI version mismatch");
@@ -222,9 +226,9 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     if (!icar) {
         const size_t qb = (v.q + 3) / 4;
         const size_t solve_smem = solve_bytes_for(v.q, v.p, v.pq);
-        // beyond ~200 the blocked factor no longer fits in shared memory: the same kernel then works out of a
-        // per-chain global scratch block (L1/L2-cached; functional large-q path, SURVEY 8(f) row 4 is the fast one)
-        v.solve_stride = solve_smem > 200 * 1024 ? (solve_smem + 64) / 8 : 0;
+        // beyond ~200 the blocked factor no longer fits in shared memory: the tiled kernel then works out of a
+        // per-chain global scratch block (32 x 32 tiles, DMMA updates)
+        v.solve_stride = solve_smem > 200 * 1024 ? (tiled_scratch_doubles(v.q, v.p) + 1) / 2 * 2 : 0;
         if (qb > SOLVE_THREADS) return set_err("RSR rank q too large (q <= 512 in this build)");
     }
     return 0;
@@ -1177,6 +1181,334 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
         return;
     }
 
+    // ---- commit state, record the draw (Chain.append, chain.py:56-74) ----
+    for (int a = tid; a < pq; a += T) v.theta[(size_t)a * Cp + c] = th[a];
+    if (tid == 0) v.tau[c] = tau;
+    if (rec_beta && rec_index >= 0 && rec_index < rec_capacity && c < v.C) {
+        const size_t row = (size_t)c * rec_capacity + rec_index;
+        for (int a = tid; a < p; a += T) rec_beta[row * p + a] = th[a];
+        if (tid == 0) rec_tau[row] = tau;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// large-q RSR solve: when Lambda no longer fits in shared memory (q > ~200) it is kept in
+// per-chain global scratch as 32 x 32 tiles and factorised by a left-looking tiled Cholesky: for block column k
+//   (A) every warp takes tiles (I, k), I >= k, and applies all updates  A_Ik -= sum_{j<k} L_Ij L_kj'  on the FP64
+//       tensor pipe (DMMA m8n8k4, accumulators in registers, operands straight from L1/L2),
+//   (B) warp 0 factorises the diagonal tile in shared memory,
+//   (C) the rows of the tiles below are solved against it (one thread per row, row in registers),
+//   (D) the finished panel is written back -- every tile is written once.
+// The right-hand side b rides along as an extra tile row, so y = L^-1 b comes out of the factorisation; the two
+// backward solves (mean and noise) are tiled the same way.  Everything around the factorisation (tau, beta, alpha,
+// commit, record) is the code of solve_logit_rsr_kernel.  Reference: logit.py:325-337, 478-485 (dgemm + dgesv).
+// ------------------------------------------------------------------------------------------------
+constexpr int TB = 32;               // tile size
+constexpr int TP = TB + 1;           // padded row length of a tile in shared memory
+constexpr int TILED_THREADS = 256;   // 8 warps
+constexpr int TILED_QMAX = 512;
+__device__ __forceinline__ size_t tile_off(int I, int J) { return ((size_t)I * (I + 1) / 2 + J) * (TB * TB); }  // J <= I
+
+static size_t tiled_scratch_doubles(int q, int p) {
+    const size_t nbk = (q + TB - 1) / TB;
+    return (nbk * (nbk + 1) / 2 + nbk) * TB * TB + nbk * TB * (size_t)p + 64;
+}
+static size_t tiled_smem_bytes(int q) {
+    const size_t nbk = (q + TB - 1) / TB;
+    return (nbk + 1) * TB * TP * sizeof(double);
+}
+
+__global__ void __launch_bounds__(TILED_THREADS, 1) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
+                                                                               double* rec_beta, double* rec_tau,
+                                                                               int rec_capacity) {
+    extern __shared__ double panel[];                 // [(nbk + 1)][TB][TP]
+    __shared__ double h[TILED_QMAX + MAX_SMALL], th[TILED_QMAX + MAX_SMALL + 4];
+    __shared__ double xm[TILED_QMAX], xe[TILED_QMAX], nrm[TILED_QMAX + 2 * MAX_SMALL];
+    __shared__ double partial[TILED_THREADS / 32][2][TB];
+    __shared__ double invd[TB], red[TILED_THREADS / 32 + 1];
+    __shared__ double small_S[MAX_SMALL * MAX_SMALL];
+    __shared__ double small_b[MAX_SMALL], small_x[MAX_SMALL], small_t[MAX_SMALL];
+    __shared__ int ok_flag;
+    const int c = blockIdx.x, tid = threadIdx.x, T = TILED_THREADS;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int p = v.p, q = v.q, r = v.r, pq = v.pq;
+    const int nbk = (q + TB - 1) / TB, q32 = nbk * TB;
+    const size_t Cp = v.Cp;
+    const HParams* hp = v.hp;
+    double* tiles = v.solve_scratch + (size_t)c * v.solve_stride;
+    double* gx = tiles + ((size_t)nbk * (nbk + 1) / 2 + nbk) * TB * TB;   // [q32][p]  K' Om X
+    const uint32_t iter = v.ctl->iter;
+    const int rec_index = v.ctl->rec_index;
+    const uint32_t gc = (uint32_t)(v.chain_offset + c);
+    const int cr = c % v.C;
+    const double* Grow = v.model == OCCU_PROBIT_RSR ? v.G0 : v.G + (size_t)c * v.M_pad;
+
+    for (int a = tid; a < pq; a += T) {
+        double hs = 0.0;
+        for (int s = 0; s < v.ksplit; s++) hs += v.Hpart[((size_t)s * Cp + c) * v.ldh + a];
+        h[a] = hs;
+        th[a] = v.theta[(size_t)a * Cp + c];
+    }
+    for (int k = tid; k < q32 + p + r; k += T) {   // normals: eta (zero padded to q32), then beta, alpha
+        const int src = k < q32 ? k : k - q32 + q;
+        double val = 0.0;
+        if (k >= q32 || k < q) {
+            if (dbg.normals) {
+                val = dbg.normals[(size_t)cr * (pq + r) + src];
+            } else {
+                Philox gph;
+                gph.init(v.seed, gc, (uint32_t)src, iter, ST_NORMALS);
+                val = gph.normal_d();
+            }
+        }
+        nrm[k] = val;
+    }
+    if (tid == 0) ok_flag = 1;
+    __syncthreads();
+
+    // ---- tau | eta   (logit.py:206-209) ----
+    {
+        double part = 0.0;
+#pragma unroll 8
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            part += th[p + i] * v.Qrsr[idx] * th[p + j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double quad = 0.0;
+            for (int w = 0; w < T / 32; w++) quad += red[w];
+            const double rate = 0.5 * quad + hp->tau_rate;
+            red[T / 32] = dbg.tau_in ? dbg.tau_in[cr] : v.gam[c] / rate;
+            if (dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
+        }
+        __syncthreads();
+    }
+    const double tau = red[T / 32];
+
+    // ---- K' Om X rows, then Lambda = K' Om K + tau Qrsr and b = K'k - (K' Om X) beta as tiles ----
+    for (int idx = tid; idx < q32 * p; idx += T) {
+        const int i = idx / p, a = idx - i * p;
+        gx[idx] = i < q ? Grow[tri(p + i, a)] : 0.0;
+    }
+    __syncthreads();
+    for (int I = 0; I <= nbk; I++) {
+        const int jmax = I < nbk ? I : nbk - 1;
+        for (int e = tid; e < (jmax + 1) * TB * TB; e += T) {
+            const int J = e / (TB * TB), rc = e - J * TB * TB, rr = rc / TB, cc = rc - rr * TB;
+            const int i = I * TB + rr, j = J * TB + cc;
+            double val;
+            if (I < nbk) {
+                if (i < q && j < q) {
+                    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+                    val = Grow[tri(p + hi, p + lo)] + tau * v.Qrsr[(size_t)hi * q + lo];
+                } else {
+                    val = i == j ? 1.0 : 0.0;   // identity padding
+                }
+            } else {                            // right-hand side row (logit.py:481)
+                val = 0.0;
+                if (rr == 0 && j < q) {
+                    double b = h[p + j];
+                    for (int a = 0; a < p; a++) b -= gx[j * p + a] * th[a];
+                    val = b;
+                    if (dbg.enabled && dbg.out.eta_b && c < v.C) dbg.out.eta_b[(size_t)c * q + j] = b;
+                }
+            }
+            tiles[tile_off(I, J) + rc] = val;
+        }
+    }
+    __syncthreads();
+    if (dbg.enabled && dbg.out.eta_prec && c < v.C)
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+            dbg.out.eta_prec[(size_t)c * q * q + idx] = tiles[tile_off(hi / TB, lo / TB) + (hi % TB) * TB + (lo % TB)];
+        }
+
+    // ---- left-looking tiled Cholesky of the augmented matrix ----
+    for (int k = 0; k < nbk; k++) {
+        // (A) updates of the tiles of block column k, one tile per warp at a time
+        for (int I = k + warp; I <= nbk; I += T / 32) {
+            double acc[4][4][2];
+            const double* src = tiles + tile_off(I, k);
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    const double2 v2 = *reinterpret_cast<const double2*>(src + (mb * 8 + g) * TB + nb * 8 + 2 * t4);
+                    acc[mb][nb][0] = v2.x;
+                    acc[mb][nb][1] = v2.y;
+                }
+            for (int j = 0; j < k; j++) {
+                const double* A = tiles + tile_off(I, j);
+                const double* B = tiles + tile_off(k, j);
+#pragma unroll 2
+                for (int ks = 0; ks < TB / 4; ks++) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) a[mb] = -A[(mb * 8 + g) * TB + ks * 4 + t4];
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) b[nb] = B[(nb * 8 + g) * TB + ks * 4 + t4];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                        for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                }
+            }
+            double* dst = panel + (size_t)(I - k) * TB * TP;
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) {
+                    dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4] = acc[mb][nb][0];
+                    dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4 + 1] = acc[mb][nb][1];
+                }
+        }
+        __syncthreads();
+        // (B) diagonal tile: warp 0, lane = row
+        if (warp == 0) {
+            double* D = panel;
+            bool good = true;
+            for (int j = 0; j < TB; j++) {
+                const double piv = D[j * TP + j];
+                if (!(piv > 0.0)) {
+                    good = false;
+                    break;
+                }
+                const double inv = rsqrt(piv), dj = piv * inv;
+                double lij = 0.0;
+                if (lane > j) lij = D[lane * TP + j] * inv;
+                __syncwarp();
+                if (lane > j) D[lane * TP + j] = lij;
+                if (lane == j) {
+                    D[j * TP + j] = dj;
+                    invd[j] = inv;
+                }
+                __syncwarp();
+                if (lane > j)
+                    for (int cc = j + 1; cc <= lane; cc++) D[lane * TP + cc] -= lij * D[cc * TP + j];
+                __syncwarp();
+            }
+            if (!good && lane == 0) ok_flag = 0;
+        }
+        __syncthreads();
+        if (!ok_flag) break;
+        // (C) rows of the tiles below: x L_kk' = a, one thread per row
+        const int nrows = (nbk - k) * TB;
+        for (int row = tid; row < nrows; row += T) {
+            double* R = panel + (size_t)(1 + row / TB) * TB * TP + (row % TB) * TP;   // row stride TP: conflict-free
+            for (int cc = 0; cc < TB; cc++) {
+                double s0 = R[cc], s1 = 0.0;          // two accumulators: the dependent chain is cc / 2 long
+                int m = 0;
+                for (; m + 1 < cc; m += 2) {
+                    s0 -= R[m] * panel[cc * TP + m];
+                    s1 -= R[m + 1] * panel[cc * TP + m + 1];
+                }
+                if (m < cc) s0 -= R[m] * panel[cc * TP + m];
+                R[cc] = (s0 + s1) * invd[cc];
+            }
+        }
+        __syncthreads();
+        // (D) write the panel back (the strictly upper part of the diagonal tile is never read)
+        for (int e = tid; e < (nbk - k + 1) * TB * TB; e += T) {
+            const int s = e / (TB * TB), rc = e - s * TB * TB;
+            tiles[tile_off(k + s, k) + rc] = panel[(size_t)s * TB * TP + (rc / TB) * TP + (rc % TB)];
+        }
+        __syncthreads();
+    }
+    if (!ok_flag) {
+        if (tid == 0) {
+            v.status[c] = 1;
+            if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+        }
+        return;
+    }
+    if (dbg.enabled && dbg.out.eta_chol && c < v.C)
+        for (int idx = tid; idx < q * q; idx += T) {
+            const int i = idx / q, j = idx - i * q;
+            dbg.out.eta_chol[(size_t)c * q * q + idx] = j <= i ? tiles[tile_off(i / TB, j / TB) + (i % TB) * TB + (j % TB)] : 0.0;
+        }
+
+    // ---- backward: L' m = y (mean) and L' e = eps, block rows from the bottom ----
+    for (int i = tid; i < q32; i += T) {
+        xm[i] = tiles[tile_off(nbk, i / TB) + (i % TB)];   // y = L^-1 b: row 0 of the extra tile row
+        xe[i] = nrm[i];
+    }
+    __syncthreads();
+    for (int k = nbk - 1; k >= 0; k--) {
+        // rhs_k -= sum_{I > k} L_Ik' x_I : warps split the tiles below, lane = column
+        double sm_ = 0.0, se_ = 0.0;
+        for (int I = k + 1 + warp; I < nbk; I += T / 32) {
+            const double* L = tiles + tile_off(I, k);
+#pragma unroll 8
+            for (int rr = 0; rr < TB; rr++) {
+                const double l = L[rr * TB + lane];
+                sm_ += l * xm[I * TB + rr];
+                se_ += l * xe[I * TB + rr];
+            }
+        }
+        partial[warp][0][lane] = sm_;
+        partial[warp][1][lane] = se_;
+        // diagonal tile into shared memory for the triangular solve
+        for (int e = tid; e < TB * TB; e += T) panel[(e / TB) * TP + (e % TB)] = tiles[tile_off(k, k) + e];
+        __syncthreads();
+        if (warp < 2) {   // warp 0: mean, warp 1: noise
+            double* x = warp == 0 ? xm : xe;
+            double rhs = x[k * TB + lane];
+            for (int w = 0; w < T / 32; w++) rhs -= partial[w][warp][lane];
+            // L_kk' x = rhs, backward: x_c = (rhs_c - sum_{m > c} L[m][c] x_m) / L[c][c]
+            for (int cc = TB - 1; cc >= 0; cc--) {
+                const double xc = __shfl_sync(0xffffffffu, rhs, cc) / panel[cc * TP + cc];
+                if (lane == cc) rhs = xc;
+                if (lane < cc) rhs -= panel[cc * TP + lane] * xc;
+            }
+            x[k * TB + lane] = rhs;
+        }
+        __syncthreads();
+    }
+    if (dbg.enabled && dbg.out.eta_mean && c < v.C)
+        for (int i = tid; i < q; i += T) dbg.out.eta_mean[(size_t)c * q + i] = xm[i];
+    for (int i = tid; i < q; i += T) th[p + i] = xm[i] + xe[i];  // eta = mean + L^-T eps
+    __syncthreads();
+
+    // ---- beta | .   A = X' Om X + b_prec,  b = X'k - (X' Om K) eta + b_prec b_mu   (logit.py:226-232) ----
+    for (int idx = tid; idx < p * p; idx += T) {
+        const int a = idx / p, b = idx - a * p;
+        small_S[idx] = ((b <= a) ? Grow[tri(a, b)] : Grow[tri(b, a)]) + hp->b_prec[idx];
+    }
+    for (int a = warp; a < p; a += T / 32) {   // one warp per row of the system: q-long dot product
+        double b = 0.0;
+        for (int j = lane; j < q; j += 32) b -= gx[j * p + a] * th[p + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) small_b[a] = b + h[a] + hp->b_pm[a];
+    }
+    __syncthreads();
+    if (dbg.enabled && c < v.C) {
+        if (dbg.out.beta_prec)
+            for (int idx = tid; idx < p * p; idx += T) dbg.out.beta_prec[(size_t)c * p * p + idx] = small_S[idx];
+        if (dbg.out.beta_b)
+            for (int a = tid; a < p; a += T) dbg.out.beta_b[(size_t)c * p + a] = small_b[a];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (small_precision_mvnorm(small_S, p, small_b, nrm + q32, small_x, small_t)) {
+            for (int a = 0; a < p; a++) th[a] = small_x[a];
+        } else {
+            ok_flag = 0;
+        }
+    }
+    __syncthreads();
+    if (!ok_flag) {
+        if (tid == 0) {
+            v.status[c] = 1;
+            if (c < v.C) atomicAdd(&v.ctl->fails, 1);
+        }
+        return;
+    }
     // ---- commit state, record the draw (Chain.append, chain.py:56-74) ----
     for (int a = tid; a < pq; a += T) v.theta[(size_t)a * Cp + c] = th[a];
     if (tid == 0) v.tau[c] = tau;
@@ -2388,7 +2720,17 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    solve_logit_rsr_kernel<<<v.Cp, solve_threads_for(v.q), smem, st>>>(v, dbg, ra, rb, rt, cap);
+    if (v.solve_stride) {   // large q: tiled factorisation out of global scratch
+        const size_t smem_t = tiled_smem_bytes(v.q);
+        static size_t configured_t = 0;
+        if (smem_t > configured_t) {
+            CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            configured_t = smem_t;
+        }
+        solve_logit_rsr_tiled_kernel<<<v.Cp, TILED_THREADS, smem_t, st>>>(v, dbg, rb, rt, cap);
+    } else {
+        solve_logit_rsr_kernel<<<v.Cp, solve_threads_for(v.q), smem, st>>>(v, dbg, ra, rb, rt, cap);
+    }
     e->launches++;
     PROF_MARK(e, KC_COUNT, st);
     CUDA_OK(cudaGetLastError());

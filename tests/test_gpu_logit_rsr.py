@@ -80,8 +80,9 @@ def test_beta_draw_vs_reference_golden_via_huge_precision():
     eng.close()
 
 
-@pytest.mark.parametrize('q,chains,gram_int8', [(7, 5, False), (64, 130, False), (230, 3, False),   # q = 230: global-scratch solve
-                                                 (7, 5, True), (64, 130, True)])                      # exact INT8 slice-GEMM Gram
+@pytest.mark.parametrize('q,chains,gram_int8', [(7, 5, False), (64, 130, False),
+                                                 (230, 3, False), (280, 2, True),     # tiled large-q solve (global scratch)
+                                                 (7, 5, True), (64, 130, True)])      # tcgen05 kind::i8 Gram
 def test_full_iteration_pieces_vs_oracle(q, chains, gram_int8):
     """Random states, several chains (incl. a padded tail and > 1 chain tile): every system of the Gaussian
     half and the z probabilities agree with the oracle to 1e-10."""
