@@ -228,7 +228,9 @@ static int fill_dims(const occu_problem_t* P, View& v) {
         const size_t solve_smem = solve_bytes_for(v.q, v.p, v.pq);
         // beyond ~200 the blocked factor no longer fits in shared memory: the tiled kernel then works out of a
         // per-chain global scratch block (32 x 32 tiles, DMMA updates)
-        v.solve_stride = solve_smem > 200 * 1024 ? (tiled_scratch_doubles(v.q, v.p) + 1) / 2 * 2 : 0;
+        const char* tq = getenv("OCCU_TILED_MIN_Q");   // tuning knob: smallest q that takes the tiled kernel
+        const bool tiled = solve_smem > 200 * 1024 || (tq && v.q >= atoi(tq));
+        v.solve_stride = tiled ? (tiled_scratch_doubles(v.q, v.p) + 1) / 2 * 2 : 0;
         if (qb > SOLVE_THREADS) return set_err("RSR rank q too large (q <= 512 in this build)");
     }
     return 0;
@@ -1218,7 +1220,7 @@ static size_t tiled_smem_bytes(int q) {
     return (nbk + 1) * TB * TP * sizeof(double);
 }
 
-__global__ void __launch_bounds__(TILED_THREADS, 1) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
+__global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
                                                                                double* rec_beta, double* rec_tau,
                                                                                int rec_capacity) {
     extern __shared__ double panel[];                 // [(nbk + 1)][TB][TP]
@@ -1368,31 +1370,32 @@ __global__ void __launch_bounds__(TILED_THREADS, 1) solve_logit_rsr_tiled_kernel
                 }
         }
         __syncthreads();
-        // (B) diagonal tile: warp 0, lane = row
-        if (warp == 0) {
+        // (B) diagonal tile, whole CTA, one barrier per column: the trailing update of column j uses the UNSCALED
+        //     column (a_ic -= a_ij a_cj / a_jj, j < c <= i); column j is scaled to l_ij = a_ij / sqrt(a_jj) during
+        //     step j + 1, when nobody reads it any more
+        {
             double* D = panel;
-            bool good = true;
-            for (int j = 0; j < TB; j++) {
-                const double piv = D[j * TP + j];
-                if (!(piv > 0.0)) {
-                    good = false;
-                    break;
+            for (int j = 0; j <= TB; j++) {
+                double piv = 1.0;
+                if (j < TB) {
+                    piv = D[j * TP + j];
+                    if (!(piv > 0.0)) {   // uniform: every thread reads the same pivot
+                        if (tid == 0) ok_flag = 0;
+                        break;
+                    }
+                    const double ipiv = 1.0 / piv;
+                    for (int e = tid; e < TB * TB; e += T) {
+                        const int i = e / TB, cc = e - i * TB;
+                        if (cc > j && i >= cc) D[i * TP + cc] -= D[i * TP + j] * D[cc * TP + j] * ipiv;
+                    }
                 }
-                const double inv = rsqrt(piv), dj = piv * inv;
-                double lij = 0.0;
-                if (lane > j) lij = D[lane * TP + j] * inv;
-                __syncwarp();
-                if (lane > j) D[lane * TP + j] = lij;
-                if (lane == j) {
-                    D[j * TP + j] = dj;
-                    invd[j] = inv;
+                if (j > 0 && tid < TB && tid >= j - 1) {   // column j - 1
+                    const double inv = invd[j - 1];
+                    D[tid * TP + j - 1] *= inv;            // row j - 1: a_jj / sqrt(a_jj) = sqrt(a_jj)
                 }
-                __syncwarp();
-                if (lane > j)
-                    for (int cc = j + 1; cc <= lane; cc++) D[lane * TP + cc] -= lij * D[cc * TP + j];
-                __syncwarp();
+                if (j < TB && tid == 0) invd[j] = rsqrt(piv);
+                __syncthreads();
             }
-            if (!good && lane == 0) ok_flag = 0;
         }
         __syncthreads();
         if (!ok_flag) break;
