@@ -48,7 +48,7 @@ def run(name, sampler, chains, steps, warmup, note):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--only', default='c1,c2,c3,c4,c5')
+    ap.add_argument('--only', default='c1,c2,c3,c4,c5,q')
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--c5-chains', default='512,2048,8192,32768')
@@ -81,6 +81,18 @@ def main():
         for chains in (int(c) for c in args.c5_chains.split(',')):
             run(f'c5_{chains}', s, chains, max(5, args.steps // 3), 5,
                 f'LogitRSR n=50000 (200x250), q=64, {chains} chains; data + constructor {ctor:.1f} s')
+    if 'q' in only:
+        # second series of SURVEY 8(d): larger RSR ranks (tiled large-q solve, tcgen05 Gram over ~34k / ~51k columns)
+        from occuspytial_b200.gibbs import _setup
+        Q, W, X, y, *_ = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random_state=0)
+        for q in (256, 512):
+            K = _setup.rsr_basis(Q, X, q=q)
+            s = LogitRSRGibbs(Q, W, X, y, random_state=10, K=K)
+            run(f'q{q}', s, 1024, max(5, args.steps // 3), 5, f'LogitRSR n=10000, q={q}, 1024 chains')
+        Q, W, X, y, *_ = make_data(n=2500, min_v=2, max_v=8, lattice=(50, 50), random_state=0)
+        s = LogitRSRGibbs(Q, W, X, y, random_state=10)          # default threshold r = 0.5
+        run('r05_2500', s, 1024, max(5, args.steps // 3), 5,
+            f'LogitRSR n=2500 (50x50), default r=0.5 -> q={s.fixed.q}, 1024 chains')
 
 
 if __name__ == '__main__':
