@@ -173,8 +173,9 @@ static size_t solve_bytes_for(int q, int p, int pq) {
 }
 
 // scratch / shared-memory sizes of the tiled large-q solve (solve_logit_rsr_tiled_kernel)
+constexpr int TILED_QMAX = 1312;     // 41 tile rows: the per-chain vectors and 9 panel slots stay within shared memory
 static size_t tiled_scratch_doubles(int q, int p);
-static size_t tiled_smem_bytes(int q);
+static size_t tiled_smem_bytes(int q, int pq);
 
 static int fill_dims(const occu_problem_t* P, View& v) {
     if (!P) return set_err("null problem");
@@ -231,7 +232,8 @@ static int fill_dims(const occu_problem_t* P, View& v) {
         const char* tq = getenv("OCCU_TILED_MIN_Q");   // tuning knob: smallest q that takes the tiled kernel
         const bool tiled = solve_smem > 200 * 1024 || (tq && v.q >= atoi(tq));
         v.solve_stride = tiled ? (tiled_scratch_doubles(v.q, v.p) + 1) / 2 * 2 : 0;
-        if (qb > SOLVE_THREADS) return set_err("RSR rank q too large (q <= 512 in this build)");
+        if (tiled ? v.q > TILED_QMAX : qb > (size_t)SOLVE_THREADS)
+            return set_err("RSR rank q too large (q <= 1312 in this build)");
     }
     return 0;
 }
@@ -1208,24 +1210,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
 constexpr int TB = 32;               // tile size
 constexpr int TP = TB + 1;           // padded row length of a tile in shared memory
 constexpr int TILED_THREADS = 256;   // 8 warps
-constexpr int TILED_QMAX = 512;
+constexpr int PANEL_SLOTS = 1 + TILED_THREADS / 32;   // diagonal tile + one tile per warp
 __device__ __forceinline__ size_t tile_off(int I, int J) { return ((size_t)I * (I + 1) / 2 + J) * (TB * TB); }  // J <= I
 
 static size_t tiled_scratch_doubles(int q, int p) {
     const size_t nbk = (q + TB - 1) / TB;
     return (nbk * (nbk + 1) / 2 + nbk) * TB * TB + nbk * TB * (size_t)p + 64;
 }
-static size_t tiled_smem_bytes(int q) {
-    const size_t nbk = (q + TB - 1) / TB;
-    return (nbk + 1) * TB * TP * sizeof(double);
+// shared memory: panel slots, then h[pq], th[pq + 4], xm[q32], xe[q32], nrm[q32 + 2 MAX_SMALL]
+static size_t tiled_smem_bytes(int q, int pq) {
+    const size_t q32 = (size_t)(q + TB - 1) / TB * TB;
+    return ((size_t)PANEL_SLOTS * TB * TP + 2 * (size_t)pq + 4 + 3 * q32 + 2 * MAX_SMALL + 8) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
                                                                                double* rec_beta, double* rec_tau,
                                                                                int rec_capacity) {
-    extern __shared__ double panel[];                 // [(nbk + 1)][TB][TP]
-    __shared__ double h[TILED_QMAX + MAX_SMALL], th[TILED_QMAX + MAX_SMALL + 4];
-    __shared__ double xm[TILED_QMAX], xe[TILED_QMAX], nrm[TILED_QMAX + 2 * MAX_SMALL];
+    extern __shared__ double panel[];                 // [PANEL_SLOTS][TB][TP], then the per-chain vectors
     __shared__ double partial[TILED_THREADS / 32][2][TB];
     __shared__ double invd[TB], red[TILED_THREADS / 32 + 1];
     __shared__ double small_S[MAX_SMALL * MAX_SMALL];
@@ -1237,6 +1238,11 @@ __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel
     const int nbk = (q + TB - 1) / TB, q32 = nbk * TB;
     const size_t Cp = v.Cp;
     const HParams* hp = v.hp;
+    double* h = panel + (size_t)PANEL_SLOTS * TB * TP;   // [pq]      U'(z - 1/2)
+    double* th = h + pq;                                 // [pq + 4]  beta, eta
+    double* xm = th + pq + 4;                            // [q32]     backward solve: mean
+    double* xe = xm + q32;                               // [q32]     backward solve: L^-T eps
+    double* nrm = xe + q32;                              // [q32 + 2 MAX_SMALL] normals
     double* tiles = v.solve_scratch + (size_t)c * v.solve_stride;
     double* gx = tiles + ((size_t)nbk * (nbk + 1) / 2 + nbk) * TB * TB;   // [q32][p]  K' Om X
     const uint32_t iter = v.ctl->iter;
@@ -1331,97 +1337,111 @@ __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel
         }
 
     // ---- left-looking tiled Cholesky of the augmented matrix ----
-    for (int k = 0; k < nbk; k++) {
-        // (A) updates of the tiles of block column k, one tile per warp at a time
-        for (int I = k + warp; I <= nbk; I += T / 32) {
-            double acc[4][4][2];
-            const double* src = tiles + tile_off(I, k);
+    for (int k = 0; k < nbk && ok_flag; k++) {
+        // tiles of block column k are processed in groups: the first group holds the diagonal tile (warp 0, slot 0)
+        // and the next 7 tiles below it, every later group 8 tiles; slots 1.. hold the group's off-diagonal tiles
+        const int nbelow = nbk - k;                       // tiles below the diagonal, incl. the right-hand-side row
+        bool first = true;
+        for (int g0 = 0; first || g0 < nbelow; g0 = first ? 7 : g0 + 8, first = false) {
+            // tile handled by this warp: first group -> warp 0: diagonal, warps 1..7: below[0..6];
+            // later groups -> below[g0 + warp]
+            const int below_idx = first ? warp - 1 : g0 + warp;
+            const int gcount = first ? min(7, nbelow) : min(8, nbelow - g0);    // off-diagonal tiles in this group
+            const bool has_tile = first ? (warp == 0 || below_idx < nbelow) : (below_idx < nbelow);
+            const int I = (first && warp == 0) ? k : k + 1 + below_idx;
+            const int slot = (first && warp == 0) ? 0 : (first ? warp : 1 + warp);
+            // (A) A_Ik -= sum_{j<k} L_Ij L_kj'
+            if (has_tile) {
+                double acc[4][4][2];
+                const double* src = tiles + tile_off(I, k);
 #pragma unroll
-            for (int mb = 0; mb < 4; mb++)
+                for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-                for (int nb = 0; nb < 4; nb++) {
-                    const double2 v2 = *reinterpret_cast<const double2*>(src + (mb * 8 + g) * TB + nb * 8 + 2 * t4);
-                    acc[mb][nb][0] = v2.x;
-                    acc[mb][nb][1] = v2.y;
-                }
-            for (int j = 0; j < k; j++) {
-                const double* A = tiles + tile_off(I, j);
-                const double* B = tiles + tile_off(k, j);
+                    for (int nb = 0; nb < 4; nb++) {
+                        const double2 v2 = *reinterpret_cast<const double2*>(src + (mb * 8 + g) * TB + nb * 8 + 2 * t4);
+                        acc[mb][nb][0] = v2.x;
+                        acc[mb][nb][1] = v2.y;
+                    }
+                for (int j = 0; j < k; j++) {
+                    const double* A = tiles + tile_off(I, j);
+                    const double* B = tiles + tile_off(k, j);
 #pragma unroll 2
-                for (int ks = 0; ks < TB / 4; ks++) {
-                    double a[4], b[4];
+                    for (int ks = 0; ks < TB / 4; ks++) {
+                        double a[4], b[4];
 #pragma unroll
-                    for (int mb = 0; mb < 4; mb++) a[mb] = -A[(mb * 8 + g) * TB + ks * 4 + t4];
+                        for (int mb = 0; mb < 4; mb++) a[mb] = -A[(mb * 8 + g) * TB + ks * 4 + t4];
 #pragma unroll
-                    for (int nb = 0; nb < 4; nb++) b[nb] = B[(nb * 8 + g) * TB + ks * 4 + t4];
+                        for (int nb = 0; nb < 4; nb++) b[nb] = B[(nb * 8 + g) * TB + ks * 4 + t4];
 #pragma unroll
-                    for (int mb = 0; mb < 4; mb++)
+                        for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-                        for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                            for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                    }
                 }
+                double* dst = panel + (size_t)slot * TB * TP;
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) {
+                        dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4] = acc[mb][nb][0];
+                        dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4 + 1] = acc[mb][nb][1];
+                    }
             }
-            double* dst = panel + (size_t)(I - k) * TB * TP;
-#pragma unroll
-            for (int mb = 0; mb < 4; mb++)
-#pragma unroll
-                for (int nb = 0; nb < 4; nb++) {
-                    dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4] = acc[mb][nb][0];
-                    dst[(mb * 8 + g) * TP + nb * 8 + 2 * t4 + 1] = acc[mb][nb][1];
-                }
-        }
-        __syncthreads();
-        // (B) diagonal tile, whole CTA, one barrier per column: the trailing update of column j uses the UNSCALED
-        //     column (a_ic -= a_ij a_cj / a_jj, j < c <= i); column j is scaled to l_ij = a_ij / sqrt(a_jj) during
-        //     step j + 1, when nobody reads it any more
-        {
-            double* D = panel;
-            for (int j = 0; j <= TB; j++) {
-                double piv = 1.0;
-                if (j < TB) {
-                    piv = D[j * TP + j];
-                    if (!(piv > 0.0)) {   // uniform: every thread reads the same pivot
-                        if (tid == 0) ok_flag = 0;
-                        break;
+            __syncthreads();
+            if (first) {
+                // (B) diagonal tile, whole CTA, one barrier per column: the trailing update of column j uses the
+                //     UNSCALED column (a_ic -= a_ij a_cj / a_jj, j < c <= i); column j is scaled to
+                //     l_ij = a_ij / sqrt(a_jj) during step j + 1, when nobody reads it any more
+                double* D = panel;
+                for (int j = 0; j <= TB; j++) {
+                    double piv = 1.0;
+                    if (j < TB) {
+                        piv = D[j * TP + j];
+                        if (!(piv > 0.0)) {   // uniform: every thread reads the same pivot
+                            if (tid == 0) ok_flag = 0;
+                            break;
+                        }
+                        const double ipiv = 1.0 / piv;
+                        for (int e = tid; e < TB * TB; e += T) {
+                            const int i = e / TB, cc = e - i * TB;
+                            if (cc > j && i >= cc) D[i * TP + cc] -= D[i * TP + j] * D[cc * TP + j] * ipiv;
+                        }
                     }
-                    const double ipiv = 1.0 / piv;
-                    for (int e = tid; e < TB * TB; e += T) {
-                        const int i = e / TB, cc = e - i * TB;
-                        if (cc > j && i >= cc) D[i * TP + cc] -= D[i * TP + j] * D[cc * TP + j] * ipiv;
-                    }
+                    if (j > 0 && tid < TB && tid >= j - 1) D[tid * TP + j - 1] *= invd[j - 1];   // column j - 1
+                    if (j < TB && tid == 0) invd[j] = rsqrt(piv);
+                    __syncthreads();
                 }
-                if (j > 0 && tid < TB && tid >= j - 1) {   // column j - 1
-                    const double inv = invd[j - 1];
-                    D[tid * TP + j - 1] *= inv;            // row j - 1: a_jj / sqrt(a_jj) = sqrt(a_jj)
-                }
-                if (j < TB && tid == 0) invd[j] = rsqrt(piv);
                 __syncthreads();
+                if (!ok_flag) break;
             }
-        }
-        __syncthreads();
-        if (!ok_flag) break;
-        // (C) rows of the tiles below: x L_kk' = a, one thread per row
-        const int nrows = (nbk - k) * TB;
-        for (int row = tid; row < nrows; row += T) {
-            double* R = panel + (size_t)(1 + row / TB) * TB * TP + (row % TB) * TP;   // row stride TP: conflict-free
-            for (int cc = 0; cc < TB; cc++) {
-                double s0 = R[cc], s1 = 0.0;          // two accumulators: the dependent chain is cc / 2 long
-                int m = 0;
-                for (; m + 1 < cc; m += 2) {
-                    s0 -= R[m] * panel[cc * TP + m];
-                    s1 -= R[m + 1] * panel[cc * TP + m + 1];
+            // (C) rows of the group's off-diagonal tiles: x L_kk' = a, one thread per row
+            if (tid < gcount * TB) {
+                double* R = panel + (size_t)(1 + tid / TB) * TB * TP + (tid % TB) * TP;   // row stride TP: conflict-free
+                for (int cc = 0; cc < TB; cc++) {
+                    double s0 = R[cc], s1 = 0.0;          // two accumulators: the dependent chain is cc / 2 long
+                    int m = 0;
+                    for (; m + 1 < cc; m += 2) {
+                        s0 -= R[m] * panel[cc * TP + m];
+                        s1 -= R[m + 1] * panel[cc * TP + m + 1];
+                    }
+                    if (m < cc) s0 -= R[m] * panel[cc * TP + m];
+                    R[cc] = (s0 + s1) * invd[cc];
                 }
-                if (m < cc) s0 -= R[m] * panel[cc * TP + m];
-                R[cc] = (s0 + s1) * invd[cc];
             }
+            __syncthreads();
+            // (D) write the group back (the strictly upper part of the diagonal tile is never read)
+            {
+                const int s0 = first ? 0 : 1, ns = gcount + (first ? 1 : 0);
+                for (int e = tid; e < ns * TB * TB; e += T) {
+                    const int s = s0 + e / (TB * TB), rc = e % (TB * TB);
+                    const int It = s == 0 ? k : k + 1 + (first ? 0 : g0) + (s - 1);
+                    tiles[tile_off(It, k) + rc] = panel[(size_t)s * TB * TP + (rc / TB) * TP + (rc % TB)];
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // (D) write the panel back (the strictly upper part of the diagonal tile is never read)
-        for (int e = tid; e < (nbk - k + 1) * TB * TB; e += T) {
-            const int s = e / (TB * TB), rc = e - s * TB * TB;
-            tiles[tile_off(k + s, k) + rc] = panel[(size_t)s * TB * TP + (rc / TB) * TP + (rc % TB)];
-        }
-        __syncthreads();
     }
+    __syncthreads();
     if (!ok_flag) {
         if (tid == 0) {
             v.status[c] = 1;
@@ -2724,7 +2744,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         configured = smem;
     }
     if (v.solve_stride) {   // large q: tiled factorisation out of global scratch
-        const size_t smem_t = tiled_smem_bytes(v.q);
+        const size_t smem_t = tiled_smem_bytes(v.q, v.pq);
         static size_t configured_t = 0;
         if (smem_t > configured_t) {
             CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
