@@ -105,7 +105,6 @@ struct View {
     int tc_Kp, tc_nsplit, tc_Mrows;
     uint8_t* Aq;            // [SA + 1][Cp][tc_Kp]   base-256 digits of omega / 8, then z
     int8_t* Bq;             // [SB][tc_Mrows][tc_Kp] balanced base-256 digits of [Z | U] / column scale
-    double* bscale;         // [ldz]       power-of-two column scales
     double* tscale;         // [tc_Mrows]  output scale per sliced row: 8 c_m (Gram columns), c_a (U columns)
     double* hshift;         // [ldh]       -colsum(U) / 2:  U'(z - 1/2) = U'z + hshift
     double* Gp;             // [tc_nsplit][Cp][M_pad] K-chunk partials (tc_nsplit > 1 only)
@@ -250,7 +249,8 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     const bool icar = v.model == OCCU_LOGIT_ICAR;
     v.Qrsr = icar ? nullptr : c.take<double>((size_t)v.q * v.q);
     v.UT = icar ? nullptr : c.take<double>((size_t)v.kq_pad * v.n_pad);
-    v.ZU = icar ? nullptr : c.take<double>((size_t)v.n_pad * v.ldz);
+    // the face-splitting design [Z | U] is the B operand of the FP64 DMMA Gram only; the tcgen05 path slices it from UT
+    v.ZU = (icar || v.int8) ? nullptr : c.take<double>((size_t)v.n_pad * v.ldz);
     v.X = icar ? c.take<double>((size_t)v.n * v.p) : nullptr;
     v.Qband = icar ? c.take<double>((size_t)v.n * (v.bw + 1)) : nullptr;
     v.eta_n = icar ? c.take<double>((size_t)v.n_pad * Cp) : nullptr;
@@ -275,7 +275,6 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     if (v.int8) {
         v.Aq = c.take<uint8_t>((size_t)(gtc::SA + 1) * Cp * v.tc_Kp);
         v.Bq = c.take<int8_t>((size_t)gtc::SB * v.tc_Mrows * v.tc_Kp);
-        v.bscale = c.take<double>(v.ldz);
         v.tscale = c.take<double>(v.tc_Mrows);
         v.hshift = c.take<double>(v.ldh);
         v.Gp = v.tc_nsplit > 1 ? c.take<double>((size_t)v.tc_nsplit * Cp * v.M_pad) : nullptr;
@@ -299,8 +298,9 @@ __global__ void build_design_kernel(View v, const double* __restrict__ X, const 
     __syncthreads();
     for (int a = threadIdx.x; a < v.pq; a += blockDim.x) {
         v.UT[(size_t)a * v.n_pad + i] = u[a];
-        v.ZU[(size_t)i * v.ldz + v.M_pad + a] = u[a];
+        if (v.ZU) v.ZU[(size_t)i * v.ldz + v.M_pad + a] = u[a];
     }
+    if (!v.ZU) return;
     for (int m = threadIdx.x; m < v.M; m += blockDim.x) {
         int a = (int)((sqrtf(8.0f * (float)m + 1.0f) - 1.0f) * 0.5f);
         while (a * (a + 1) / 2 > m) a--;
@@ -2862,14 +2862,13 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     e->slices_valid = false;
     e->omega_in_slices = false;
     if (v.int8) {
-        // slice [Z | U] once, encode the TMA descriptors of the two operand arrays
+        // slice [Z | U] once (formed on the fly from U'), encode the TMA descriptors of the two operand arrays
         e->geo = gtc::make_geometry(v.n, v.Cp, v.M, v.pq, TC_BN);
         const gtc::Geometry& g = e->geo;
-        gtc::column_scale_kernel<<<(v.ldz + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.ldz, v.bscale);
-        gtc::slice_b_kernel<<<dim3((g.Kp + 255) / 256, g.Mrows), 256, 0, st>>>(v.ZU, v.n, g.Kp, v.ldz, v.M, g.Mg_pad, v.pq, v.M_pad,
-                                                                               g.Mrows, v.bscale, v.tscale, v.Bq);
-        gtc::hshift_kernel<<<(v.ldh + 127) / 128, 128, 0, st>>>(v.ZU, v.n, v.ldz, v.M_pad, v.pq, v.ldh, v.hshift);
-        e->launches += 3;
+        gtc::slice_rows_from_ut_kernel<<<g.Mrows, 256, 0, st>>>(v.UT, v.n, v.n_pad, g.Kp, v.M, g.Mg_pad, v.pq, g.Mrows, v.tscale,
+                                                                 v.Bq);
+        gtc::hshift_from_ut_kernel<<<(v.ldh + 127) / 128, 128, 0, st>>>(v.UT, v.n, v.n_pad, v.pq, v.ldh, v.hshift);
+        e->launches += 2;
         FAIL_IF(cudaMemsetAsync(v.Aq, 0, (size_t)(gtc::SA + 1) * v.Cp * g.Kp, st));
         FAIL_IF(cudaMemsetAsync(v.G, 0, (size_t)v.Cp * v.M_pad * 8, st));
         FAIL_IF(cudaMemsetAsync(v.tc_err, 0, sizeof(int), st));

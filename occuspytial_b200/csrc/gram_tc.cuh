@@ -582,6 +582,78 @@ __global__ void slice_b_kernel(const double* __restrict__ ZU, int n, int Kp, int
     }
 }
 
+// ---- the same set-up from U' alone (the engine's path): the face-splitting design Z[i][vech(a, b)] = u_ia u_ib is
+// never materialised -- at q = 1256 it would be 64 GB of FP64 -- its entries are formed on the fly from the rows of
+// UT[a][i] = U[i][a] (coalesced over sites), rounded once exactly as a stored Z would be.
+// Row r of the sliced operand: r < M -> pair (a, b) = unvech(r), b <= a;  Mg_pad <= r < Mg_pad + pq -> column r - Mg_pad
+// of U;  anything else is padding (zeros, scale 0).
+__device__ __forceinline__ void unvech(int m, int& a, int& b) {
+    a = (int)((sqrt(8.0 * (double)m + 1.0) - 1.0) * 0.5);
+    while ((long long)a * (a + 1) / 2 > m) a--;
+    while ((long long)(a + 1) * (a + 2) / 2 <= m) a++;
+    b = m - (int)((long long)a * (a + 1) / 2);
+}
+
+// One CTA per sliced row: c = power-of-two scale of the row (see column_scale_kernel), then the SB digit planes and
+// the output scale (8 c for Gram rows, c for U rows).
+__global__ void __launch_bounds__(256) slice_rows_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int Kp, int M,
+                                                                 int Mg_pad, int pq, int Mrows,
+                                                                 double* __restrict__ scale_out, int8_t* __restrict__ Bq) {
+    __shared__ double red[8];
+    __shared__ double cs;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const double* ua = nullptr;
+    const double* ub = nullptr;
+    if (row < M) {
+        int a, b;
+        unvech(row, a, b);
+        ua = UT + (size_t)a * ldu;
+        ub = UT + (size_t)b * ldu;
+    } else if (row >= Mg_pad && row < Mg_pad + pq) {
+        ua = UT + (size_t)(row - Mg_pad) * ldu;
+    }
+    double mx = 0.0;
+    if (ua)
+        for (int i = tid; i < n; i += 256) mx = fmax(mx, fabs(ub ? ua[i] * ub[i] : ua[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double m8 = 0.0;
+        for (int w = 0; w < 8; w++) m8 = fmax(m8, red[w]);
+        int e = 0;
+        if (m8 > 0.0) {
+            const double f = frexp(m8, &e);
+            e += f > 0.99 ? 2 : 1;
+        }
+        cs = ldexp(1.0, e);
+        scale_out[row] = !ua ? 0.0 : (ub ? OMEGA_SCALE * cs : cs);
+    }
+    __syncthreads();
+    const double mult = (double)(1LL << (8 * SB)) / cs;   // exact: cs is a power of two
+    for (int i = tid; i < Kp; i += 256) {
+        long long q = 0;
+        if (ua && i < n) q = llrint((ub ? ua[i] * ub[i] : ua[i]) * mult);
+#pragma unroll
+        for (int t = SB; t >= 1; t--) {
+            const long long d = ((q + 128) & 0xFF) - 128;
+            q = (q - d) >> 8;
+            Bq[((size_t)(t - 1) * Mrows + row) * Kp + i] = (int8_t)d;
+        }
+    }
+}
+
+// hshift[a] = -1/2 sum_i U[i][a] (fixed order) from the rows of UT
+__global__ void hshift_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int pq, int ldh, double* __restrict__ hshift) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= ldh) return;
+    double acc = 0.0;
+    if (a < pq)
+        for (int i = 0; i < n; i++) acc += UT[(size_t)a * ldu + i];
+    hshift[a] = -0.5 * acc;
+}
+
 // Aq[s][c][i] = digit s+1 of floor(omega[i][c] 2^45) (48-bit fixed point of omega / 8), Aq[Z_SLICE][c][i] = z[i][c].
 // 32 x 32 tile transpose from the chain-minor layout of the sweep state.
 __global__ void __launch_bounds__(256) slice_a_kernel(const double* __restrict__ omega, const uint8_t* __restrict__ z, int n,

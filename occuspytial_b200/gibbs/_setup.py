@@ -10,6 +10,7 @@ from scipy import sparse
 from scipy.sparse.linalg import LinearOperator, eigsh
 
 DENSE_LIMIT = 3000  # up to this many sites the reference's dense eigh is reproduced exactly
+DEVICE_DENSE_LIMIT = 20000  # up to this many sites the dense eigen-problem is solved on the GPU when many pairs are wanted
 
 
 def partition(y_data, n):
@@ -57,7 +58,10 @@ def rsr_basis(Q, X, r=0.5, q=None):
 
     n <= DENSE_LIMIT: dense ``eigh`` exactly as the reference.  Larger n: Lanczos (``eigsh``, 'LA')
     on the implicit operator; with only a threshold ``r`` the number of eigenpairs is grown until the
-    smallest one falls below ``r``.
+    smallest one falls below ``r``.  When many pairs are wanted (q > 256, or a threshold, which at the default
+    r = 0.5 keeps ~ n / 8 of them) and a CUDA device is present, the dense problem is solved on the device instead
+    (FP64 ``eigh``, seconds at n = 10^4 where the reference's host ``eigh`` takes ten minutes and Lanczos with
+    > 1000 pairs is slower still) -- SURVEY.md 8(f) row 1.
     """
     n = X.shape[0]
     if q is None or not q:
@@ -77,6 +81,17 @@ def rsr_basis(Q, X, r=0.5, q=None):
                 raise ValueError('The Moran Operator Matrix of the data has no positive eigenvalues. '
                                  'Set threshold to a lower value')
         return np.ascontiguousarray(v[:, -qq:])
+    if (not q or int(q) > 256) and n <= DEVICE_DENSE_LIMIT:
+        dense = _device_moran_eigh(A, X, XtX_inv)
+        if dense is not None:
+            w, v = dense
+            if q:
+                return np.ascontiguousarray(v[:, -int(q):])
+            keep = w >= r
+            if not keep.any():
+                raise ValueError('The Moran Operator Matrix of the data has no positive eigenvalues. '
+                                 'Set threshold to a lower value')
+            return np.ascontiguousarray(v[:, keep])
     if q:
         w, v = eigsh(op, k=int(q), which='LA')
         order = np.argsort(w)
@@ -93,6 +108,31 @@ def rsr_basis(Q, X, r=0.5, q=None):
                                  'Set threshold to a lower value')
             return np.ascontiguousarray(v[:, keep])
         k = min(2 * k, n - 2)
+
+
+def _device_moran_eigh(A, X, XtX_inv):
+    """All eigenpairs (ascending) of n * P A P / sum(A) by a dense FP64 ``eigh`` on the current CUDA device, or None
+    when no device (or not enough device memory) is available.  Set-up only: this is a plain library call."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        n = A.shape[0]
+        dev = torch.device('cuda')
+        Xd = torch.as_tensor(np.ascontiguousarray(X), dtype=torch.float64, device=dev)
+        Ad = torch.as_tensor(A.toarray(), dtype=torch.float64, device=dev)
+        Pd = -(Xd @ torch.as_tensor(XtX_inv, dtype=torch.float64, device=dev) @ Xd.T)
+        Pd.diagonal().add_(1.0)
+        omega = (Pd.T @ (Ad @ Pd)) * (n / float(A.sum()))
+        del Ad, Pd
+        omega = 0.5 * (omega + omega.T)
+        w, v = torch.linalg.eigh(omega)
+        out = w.cpu().numpy(), v.cpu().numpy()
+        del omega, w, v
+        torch.cuda.empty_cache()
+        return out
+    except (ImportError, RuntimeError):
+        return None
 
 
 def verify_singular(Q):
