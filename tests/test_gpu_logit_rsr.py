@@ -218,3 +218,49 @@ def test_posterior_vs_reference_chains():
             assert abs(mr - mm) < 3.0 * np.hypot(sr, sm), (name, mr, mm, sr, sm)
             # quantiles: MCSE of a quantile is larger than of the mean; allow 5 x
             assert np.all(np.abs(qr - qm) < 6.0 * np.hypot(sr, sm) + 0.02 * np.abs(qr)), (name, qr, qm)
+
+
+def test_large_rank_tiled_solve_vs_oracle():
+    """q = 600 (19 tile rows: several panel groups per block column of the tiled solve, a 180k-column Gram on the
+    tcgen05 path): Lambda, b, the Cholesky factor, the conditional mean and the draw agree with the oracle."""
+    from occuspytial_b200 import LogitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from oracle import sweep as S
+    q, chains = 600, 2
+    Q, W, X, y, *_ = make_data(n=800, min_v=1, max_v=5, ns=400, p=3, q=3, random_state=5)
+    s = LogitRSRGibbs(Q, W, X, y, random_state=2, q=q)
+    f = s.fixed
+    rng = np.random.default_rng(6)
+    eng = s._make_engine(chains, seed=12, debug=True, gram_int8=True)
+    st = dict(alpha=rng.normal(size=(chains, 3)), beta=rng.normal(size=(chains, 3)), tau=rng.uniform(0.5, 2, chains),
+              eta=rng.normal(size=(chains, q)) * 0.3)
+    eng.set_start(st)
+    eng.debug_site_half()
+    z = eng.get_field(_lib.F_Z).astype(float)
+    omega = eng.get_field(_lib.F_OMEGA)
+    normals = rng.normal(size=(chains, q + 3 + 3))
+    out = eng.debug_gaussian_half(normals=normals, tau=st['tau'])
+    assert out['fails'] == 0
+    eta_new = eng.get_field(_lib.F_ETA)
+    for c in range(chains):
+        Lam, b = S.eta_rsr_system(f.K, X, omega[c], z[c] - 0.5, st['beta'][c], st['tau'][c], f.Q)
+        np.testing.assert_allclose(out['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
+        np.testing.assert_allclose(out['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+        eta_o, mean_o, L_o = S.gaussian_from_system(Lam, b, normals[c, :q])
+        np.testing.assert_allclose(out['eta_chol'][c], L_o, rtol=1e-9, atol=1e-11 * np.abs(L_o).max())
+        np.testing.assert_allclose(out['eta_mean'][c], mean_o, rtol=1e-8, atol=1e-10 * np.abs(mean_o).max())
+        np.testing.assert_allclose(eta_new[c], eta_o, rtol=1e-8, atol=1e-10 * np.abs(eta_o).max())
+    eng.close()
+
+
+def test_default_threshold_at_moderate_size():
+    """The reference's default call LogitRSRGibbs(Q, W, X, y) (r = 0.5 -> q ~ n / 8, logit.py:409-411) beyond the
+    shared-memory solve: n = 2500 gives q = 317.  Runs, keeps every chain positive definite and moves alpha."""
+    from occuspytial_b200 import LogitRSRGibbs
+    from occuspytial_b200.utils import make_data
+    Q, W, X, y, alpha, *_ = make_data(n=2500, min_v=2, max_v=8, lattice=(50, 50), random_state=0)
+    s = LogitRSRGibbs(Q, W, X, y, random_state=10)
+    assert s.fixed.q > 256
+    post = s.sample(60, burnin=30, chains=32, progressbar=False)
+    assert post['alpha'].shape == (32, 30, 3) and np.all(np.isfinite(post['tau'])) and np.all(post['tau'] > 0)
+    assert np.linalg.norm(post['alpha'].mean(axis=(0, 1)) - alpha) < 0.6
