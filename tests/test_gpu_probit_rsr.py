@@ -48,12 +48,13 @@ def test_probit_iteration_vs_reference_golden():
     eng.close()
 
 
-def test_probit_pieces_vs_oracle_multichain():
+@pytest.mark.parametrize('chains,q', [(130, 21), (3, 250)])   # q = 250: tiled large-q solve with the shared unit-weight Gram
+def test_probit_pieces_vs_oracle_multichain(chains, q):
     from occuspytial_b200 import ProbitRSRGibbs, _lib
     from occuspytial_b200.utils import make_data
     from oracle import sweep as S
     Q, W, X, y, *_ = make_data(n=300, min_v=1, max_v=6, ns=170, p=4, q=3, random_state=3)
-    chains, q, p, r = 130, 21, 4, 3
+    p, r = 4, 3
     s = ProbitRSRGibbs(Q, W, X, y, random_state=2, q=q)
     f = s.fixed
     prob = s._problem_arrays()
@@ -74,7 +75,7 @@ def test_probit_pieces_vs_oracle_multichain():
     eta_new, beta_new, alpha_new = eng.get_field(_lib.F_ETA), eng.get_field(_lib.F_BETA), eng.get_field(_lib.F_ALPHA)
     vptr, Wd, yd = prob['visit_ptr'], prob['W_rows'], prob['y_rows'].astype(float)
     KTK, XTXb = f.K.T @ f.K, X.T @ X + f.b_prec
-    for c in (0, 1, 63, 64, 127, 128, 129):
+    for c in (range(chains) if chains <= 8 else (0, 1, 63, 64, 127, 128, 129)):
         spatial = f.K @ st['eta'][c]
         ob = S.probit_omega_b(X, st['beta'][c], spatial, st['eps'][c], z[c], u_site[c])
         np.testing.assert_allclose(omega[c], ob, rtol=1e-10, atol=1e-12)
