@@ -997,16 +997,35 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
         gx[idx] = i < q ? Grow[tri(p + i, a)] : 0.0;
     }
     __syncthreads();
-    {   // Lambda = K' Om K + tau Qrsr, flattened over the packed lower triangle so that every thread has several
-        // independent loads in flight (a row-by-row loop serialises 64 global-load latencies)
-        const int ntri = q * (q + 1) / 2;
-#pragma unroll 4
-        for (int t = tid; t < ntri; t += T) {
-            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while (i * (i + 1) / 2 > t) i--;
-            while ((i + 1) * (i + 2) / 2 <= t) i++;
-            const int j = t - i * (i + 1) / 2;
-            Bs[bidx(i >> 2, j >> 2) + (i & 3) * 4 + (j & 3)] = Grow[tri(p + i, p + j)] + tau * v.Qrsr[(size_t)i * q + j];
+    {   // Lambda = K' Om K + tau Qrsr.  One warp per row (contiguous in the packed Gram), four rows in flight per
+        // warp: the loads of a batch are issued before any is consumed (a plain row-by-row loop serialises q
+        // global-load latencies; decoding (i, j) from a flat triangle index costs ~30 instructions per element)
+        const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
+        for (int i0 = warp; i0 < q; i0 += 4 * nwarp) {
+            double gv[4][2], qv[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * nwarp;
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    const int j = lane + 32 * w;
+                    const bool on = i < q && j <= i;
+                    gv[u][w] = on ? Grow[tri(p + i, p) + j] : 0.0;
+                    qv[u][w] = on ? v.Qrsr[(size_t)i * q + j] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * nwarp;
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    const int j = lane + 32 * w;
+                    if (i < q && j <= i) Bs[bidx(i >> 2, j >> 2) + (i & 3) * 4 + (j & 3)] = gv[u][w] + tau * qv[u][w];
+                }
+            }
+            for (int i = i0; i < q && i < i0 + 4 * nwarp; i += nwarp)   // columns beyond 64 (q > 64)
+                for (int j = 64 + lane; j <= i; j += 32)
+                    Bs[bidx(i >> 2, j >> 2) + (i & 3) * 4 + (j & 3)] = Grow[tri(p + i, p) + j] + tau * v.Qrsr[(size_t)i * q + j];
         }
     }
     for (int i = q + tid; i < q4; i += T) Bs[bidx(i >> 2, i >> 2) + (i & 3) * 5] = 1.0;  // identity padding
