@@ -1322,30 +1322,48 @@ __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel
         gx[idx] = i < q ? Grow[tri(p + i, a)] : 0.0;
     }
     __syncthreads();
-    for (int I = 0; I <= nbk; I++) {
-        const int jmax = I < nbk ? I : nbk - 1;
-        for (int e = tid; e < (jmax + 1) * TB * TB; e += T) {
-            const int J = e / (TB * TB), rc = e - J * TB * TB, rr = rc / TB, cc = rc - rr * TB;
-            const int i = I * TB + rr, j = J * TB + cc;
-            double val;
-            if (I < nbk) {
-                if (i < q && j < q) {
-                    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
-                    val = Grow[tri(p + hi, p + lo)] + tau * v.Qrsr[(size_t)hi * q + lo];
-                } else {
-                    val = i == j ? 1.0 : 0.0;   // identity padding
-                }
-            } else {                            // right-hand side row (logit.py:481)
-                val = 0.0;
-                if (rr == 0 && j < q) {
-                    double b = h[p + j];
-                    for (int a = 0; a < p; a++) b -= gx[j * p + a] * th[a];
-                    val = b;
-                    if (dbg.enabled && dbg.out.eta_b && c < v.C) dbg.out.eta_b[(size_t)c * q + j] = b;
+    for (int I = 0; I < nbk; I++) {   // Lambda tiles: four elements per thread in flight (read-only loads first)
+        const int count = (I + 1) * TB * TB;
+        for (int e0 = tid; e0 < count; e0 += 4 * T) {
+            double gv[4], qv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * T;
+                gv[u] = 0.0;
+                qv[u] = 0.0;
+                if (e < count) {
+                    const int J = e / (TB * TB), rc = e - J * TB * TB, rr = rc / TB, cc = rc - rr * TB;
+                    const int i = I * TB + rr, j = J * TB + cc;
+                    if (i < q && j < q) {
+                        const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+                        gv[u] = __ldg(Grow + tri(p + hi, p + lo));
+                        qv[u] = __ldg(v.Qrsr + (size_t)hi * q + lo);
+                    } else {
+                        gv[u] = i == j ? 1.0 : 0.0;   // identity padding
+                    }
                 }
             }
-            tiles[tile_off(I, J) + rc] = val;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * T;
+                if (e < count) {
+                    const int J = e / (TB * TB), rc = e - J * TB * TB;
+                    tiles[tile_off(I, J) + rc] = gv[u] + tau * qv[u];
+                }
+            }
         }
+    }
+    for (int e = tid; e < nbk * TB * TB; e += T) {   // right-hand side row (logit.py:481): row 0 of tile row nbk
+        const int J = e / (TB * TB), rc = e - J * TB * TB, rr = rc / TB, cc = rc - rr * TB;
+        const int j = J * TB + cc;
+        double val = 0.0;
+        if (rr == 0 && j < q) {
+            double b = h[p + j];
+            for (int a = 0; a < p; a++) b -= gx[j * p + a] * th[a];
+            val = b;
+            if (dbg.enabled && dbg.out.eta_b && c < v.C) dbg.out.eta_b[(size_t)c * q + j] = b;
+        }
+        tiles[tile_off(nbk, J) + rc] = val;
     }
     __syncthreads();
     if (dbg.enabled && dbg.out.eta_prec && c < v.C)
@@ -1420,10 +1438,9 @@ __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel
                             if (tid == 0) ok_flag = 0;
                             break;
                         }
-                        const double ipiv = 1.0 / piv;
-                        for (int e = tid; e < TB * TB; e += T) {
-                            const int i = e / TB, cc = e - i * TB;
-                            if (cc > j && i >= cc) D[i * TP + cc] -= D[i * TP + j] * D[cc * TP + j] * ipiv;
+                        if (lane > j) {   // lane = row, warp = column group (columns j + 1 + warp, + 8, ... <= row)
+                            const double lij = D[lane * TP + j] / piv;
+                            for (int cc = j + 1 + warp; cc <= lane; cc += T / 32) D[lane * TP + cc] -= lij * D[cc * TP + j];
                         }
                     }
                     if (j > 0 && tid < TB && tid >= j - 1) D[tid * TP + j - 1] *= invd[j - 1];   // column j - 1
