@@ -1228,7 +1228,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const Vi
 // ------------------------------------------------------------------------------------------------
 constexpr int TB = 32;               // tile size
 constexpr int TP = TB + 1;           // padded row length of a tile in shared memory
-constexpr int TILED_THREADS = 256;   // 8 warps
+#ifndef TILED_THREADS_N
+#define TILED_THREADS_N 256
+#endif
+constexpr int TILED_THREADS = TILED_THREADS_N;   // 8 warps
+constexpr int TILED_WARPS = TILED_THREADS / 32;
 constexpr int PANEL_SLOTS = 1 + TILED_THREADS / 32;   // diagonal tile + one tile per warp
 __device__ __forceinline__ size_t tile_off(int I, int J) { return ((size_t)I * (I + 1) / 2 + J) * (TB * TB); }  // J <= I
 
@@ -1242,7 +1246,7 @@ static size_t tiled_smem_bytes(int q, int pq) {
     return ((size_t)PANEL_SLOTS * TB * TP + 2 * (size_t)pq + 4 + 3 * q32 + 2 * MAX_SMALL + 8) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
+__global__ void __launch_bounds__(TILED_THREADS, 512 / TILED_THREADS) solve_logit_rsr_tiled_kernel(const View v, const SolveDebug dbg,
                                                                                double* rec_beta, double* rec_tau,
                                                                                int rec_capacity) {
     extern __shared__ double panel[];                 // [PANEL_SLOTS][TB][TP], then the per-chain vectors
@@ -1376,14 +1380,15 @@ __global__ void __launch_bounds__(TILED_THREADS, 2) solve_logit_rsr_tiled_kernel
     // ---- left-looking tiled Cholesky of the augmented matrix ----
     for (int k = 0; k < nbk && ok_flag; k++) {
         // tiles of block column k are processed in groups: the first group holds the diagonal tile (warp 0, slot 0)
-        // and the next 7 tiles below it, every later group 8 tiles; slots 1.. hold the group's off-diagonal tiles
+        // and the next TILED_WARPS - 1 tiles below it, every later group TILED_WARPS tiles; slots 1.. hold the group's
+        // off-diagonal tiles
         const int nbelow = nbk - k;                       // tiles below the diagonal, incl. the right-hand-side row
         bool first = true;
-        for (int g0 = 0; first || g0 < nbelow; g0 = first ? 7 : g0 + 8, first = false) {
+        for (int g0 = 0; first || g0 < nbelow; g0 = first ? TILED_WARPS - 1 : g0 + TILED_WARPS, first = false) {
             // tile handled by this warp: first group -> warp 0: diagonal, warps 1..7: below[0..6];
             // later groups -> below[g0 + warp]
             const int below_idx = first ? warp - 1 : g0 + warp;
-            const int gcount = first ? min(7, nbelow) : min(8, nbelow - g0);    // off-diagonal tiles in this group
+            const int gcount = first ? min(TILED_WARPS - 1, nbelow) : min(TILED_WARPS, nbelow - g0);   // off-diagonal tiles
             const bool has_tile = first ? (warp == 0 || below_idx < nbelow) : (below_idx < nbelow);
             const int I = (first && warp == 0) ? k : k + 1 + below_idx;
             const int slot = (first && warp == 0) ? 0 : (first ? warp : 1 + warp);
