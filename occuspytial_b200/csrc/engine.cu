@@ -387,11 +387,17 @@ __global__ void to_chain_major_kernel(const T* __restrict__ src, T* __restrict__
 // resident CTAs per SM the register allocation aims at: 8 (64 registers) for the usual r <= 4, fewer when the
 // r (r + 1) / 2 + r FP64 accumulators no longer fit
 constexpr int site_min_blocks(int r) { return r <= 4 ? 8 : (r <= 6 ? 5 : 3); }
-template <int R, typename PGT, bool SLICES>
+//  FUSE_PSI: psi = [X K] theta of the tile is computed here, on the FP64 tensor pipe (DMMA m8n8k4: 8 sites x 32 chains
+//          per warp and step, operands straight from L1/L2), instead of by a separate GEMM that writes psi [n x chains]
+//          to HBM for this kernel to read back: the DMMA work hides under the ALU-bound PG sampling of the other warps.
+constexpr int PSI_SUB = 8;   // sites per DMMA sub-tile
+template <int R, typename PGT, bool SLICES, bool FUSE_PSI>
 __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     extern __shared__ __align__(16) unsigned char site_smem[];
     PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // column tid is private to thread tid
+    // FUSE_PSI: FP64 psi of the current sub-tile, [PSI_SUB][CHAIN_TILE]; a warp only touches its own 32 columns
+    double (*psi_d)[CHAIN_TILE] = reinterpret_cast<double(*)[CHAIN_TILE]>(site_smem + sizeof(PGT) * SITE_TILE * CHAIN_TILE);
     const int tid = threadIdx.x;
     const uint32_t iter = v.ctl->iter;
     const bool first = v.ctl->first != 0;
@@ -408,10 +414,41 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
 
     // ---- phase 1: z | . ----
     uint64_t zbits = 0ull;
-    for (int i = i0; i < i1; i++) {
+    static_assert(SITE_TILE % PSI_SUB == 0, "whole DMMA sub-tiles");
+    for (int ib = i0; ib < i1; ib += PSI_SUB) {
+    if (FUSE_PSI) {
+        // psi[ib .. ib + 8)[32 chains of this warp] = U theta:  D (8 sites x 8 chains) += A (8 x 4: UT'[site][k]) B (4 x 8:
+        // theta[k][chain]); rows of UT and theta beyond pq are zero up to kq_pad
+        const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+        const int cw = c - lane;   // first chain of this warp
+        double acc[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) acc[nb][0] = acc[nb][1] = 0.0;
+        const double* ua = v.UT + (size_t)t4 * v.n_pad + ib + g;       // n_pad >= i0 + SITE_TILE: no bounds check
+        const double* tb = v.theta + (size_t)t4 * Cp + cw + g;
+        const int ksteps = (v.pq + 3) >> 2;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ks++) {
+            const double a = ua[(size_t)ks * 4 * v.n_pad];
+            double b[4];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) b[nb] = tb[(size_t)ks * 4 * Cp + nb * 8];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[nb][0], acc[nb][1], a, b[nb]);
+        }
+        __syncwarp();   // the previous sub-tile's readers are done
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            psi_d[g][(tid & ~31) + nb * 8 + 2 * t4] = acc[nb][0];
+            psi_d[g][(tid & ~31) + nb * 8 + 2 * t4 + 1] = acc[nb][1];
+        }
+        __syncwarp();
+    }
+    for (int i = ib; i < min(ib + PSI_SUB, i1); i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
-        const double psi = v.psi[off];
+        const double psi = FUSE_PSI ? psi_d[i - ib][tid] : v.psi[off];
+        if (FUSE_PSI && v.zprob) v.psi[off] = psi;   // debug engines keep psi readable
         int zc;
         if (first) {
             zc = v.z[off];
@@ -446,6 +483,7 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
         zbits |= (uint64_t)zc << (i - i0);
         arg_s[i - i0][tid] = (PGT)psi;
     }
+    }  // sub-tiles
 
     // ---- phase 2: per-lane stream of PG draws ----
     double acc[NV];
@@ -2590,17 +2628,28 @@ __global__ void __launch_bounds__(128, 5) solve_logit_icar_mma_kernel(const View
 // ------------------------------------------------------------------------------------------------
 // host-side drivers
 // ------------------------------------------------------------------------------------------------
-template <typename PGT, bool SLICES>
+// The RSR logit sweep computes psi inside the site pass (FUSE_PSI) in production precision; the FP64-sampler
+// validation build and OCCU_FUSE_PSI=0 keep the separate GEMM.
+static bool fuse_psi(const occu_engine* e) {
+    static int allowed = -1;
+    if (allowed < 0) {
+        const char* s = getenv("OCCU_FUSE_PSI");
+        allowed = s ? atoi(s) : 1;
+    }
+    return allowed && e->v.model == OCCU_LOGIT_RSR && !e->pg_fp64;
+}
+
+template <typename PGT, bool SLICES, bool FUSE_PSI>
 static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
-    const size_t smem = (size_t)SITE_TILE * CHAIN_TILE * sizeof(PGT);
+    const size_t smem = (size_t)SITE_TILE * CHAIN_TILE * sizeof(PGT) + (FUSE_PSI ? PSI_SUB * CHAIN_TILE * sizeof(double) : 0);
     switch (v.r) {
 #define CASE(R)                                                                                                      \
     case R:                                                                                                          \
         if (smem > 48 * 1024)                                                                                        \
-            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT, SLICES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        site_pass_logit_kernel<R, PGT, SLICES><<<grid, CHAIN_TILE, smem, st>>>(v);                                    \
+            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT, SLICES, FUSE_PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        site_pass_logit_kernel<R, PGT, SLICES, FUSE_PSI><<<grid, CHAIN_TILE, smem, st>>>(v);                          \
         break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
@@ -2624,14 +2673,17 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
         e->launches++;
     } else if (v.int8) {
         // the site pass writes the digits of (omega, z) for the tcgen05 Gram itself
-        if (e->pg_fp64) launch_site_pass_logit<double, true>(e, st);
-        else launch_site_pass_logit<float, true>(e, st);
+        if (e->pg_fp64) launch_site_pass_logit<double, true, false>(e, st);
+        else if (fuse_psi(e)) launch_site_pass_logit<float, true, true>(e, st);
+        else launch_site_pass_logit<float, true, false>(e, st);
         e->slices_valid = true;
         e->omega_in_slices = v.zprob == nullptr;
     } else if (e->pg_fp64) {
-        launch_site_pass_logit<double, false>(e, st);
+        launch_site_pass_logit<double, false, false>(e, st);
+    } else if (fuse_psi(e)) {
+        launch_site_pass_logit<float, false, true>(e, st);
     } else {
-        launch_site_pass_logit<float, false>(e, st);
+        launch_site_pass_logit<float, false, false>(e, st);
     }
 }
 
@@ -3039,6 +3091,8 @@ int occu_get_field(occu_engine_t* e, int field, void* dst, void* stream) {
     void* ptr; int d, u8;
     if (field_info(e, field, &ptr, &d, &u8)) return -1;
     if (field == OCCU_F_OMEGA && materialise_omega(e, st)) return -1;
+    // psi lives only inside the site pass when it is fused there (non-debug engines): recompute it from the current state
+    if (field == OCCU_F_PSI && fuse_psi(e) && !e->debug && launch_psi_gemm(e, st)) return -1;
     const View& v = e->v;
     dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
     if (u8) to_chain_major_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)ptr, (uint8_t*)dst, v.C, v.Cp, d);
@@ -3087,7 +3141,7 @@ int occu_sweep_enqueue(occu_engine_t* e, int n_iters, double* rec_alpha, double*
     memset(&sdbg, 0, sizeof(sdbg));
     for (int it = 0; it < n_iters; it++) {
         PROF_MARK(e, KC_PSI_GEMM, st);
-        if (launch_psi_gemm(e, st)) return -1;
+        if (!fuse_psi(e) && launch_psi_gemm(e, st)) return -1;   // fused into the site pass otherwise
         PROF_MARK(e, KC_SITE_PASS, st);
         launch_site_pass(e, sdbg, st);
         if (launch_gaussian_half(e, dbg, rec_alpha, rec_beta, rec_tau, rec_capacity, st)) return -1;

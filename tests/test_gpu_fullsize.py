@@ -34,13 +34,15 @@ def test_full_size_invariants(big):
     cls = s.fixed.site_class
     assert np.all(z[:, cls == 2] == 1)                      # detection implies occupancy (base.py:118)
     assert 0 < z[:, cls == 1].mean() < 1 and 0 < z[:, cls == 0].mean() < 1
-    # psi = X beta + K eta on every chain, to rounding (the DMMA GEMM at full size)
+    # psi = X beta + K eta on every chain, to rounding (the DMMA GEMM at full size; a non-debug engine computes psi
+    # inside the site pass, so reading the field evaluates it for the current state)
     beta, eta = eng.get_field(_lib.F_BETA), eng.get_field(_lib.F_ETA)
-    eng.sweep(1)                                            # psi of the state just read is computed first ...
     psi = eng.get_field(_lib.F_PSI)
     ref = beta @ s.X.T + eta @ s.fixed.K.T
     np.testing.assert_allclose(psi, ref, rtol=1e-11, atol=1e-11)
-    # ... and omega_b ~ PG(1, psi): law of large numbers over 4 x 10^7 draws against the analytic mean / variance
+    # omega_b ~ PG(1, psi) of the sweep that starts from this state (psi formed by the fused DMMA product of the site
+    # pass): law of large numbers over 4 x 10^7 draws against the analytic mean / variance
+    eng.sweep(1)
     omega = eng.get_field(_lib.F_OMEGA)
     assert np.all(omega > 0) and np.all(np.isfinite(omega))
     resid = (omega - S.pg1_mean(psi)) / np.sqrt(S.pg1_var(psi))
