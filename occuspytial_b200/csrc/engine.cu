@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
         const double* ua = v.UT + (size_t)t4 * v.n_pad + ib + g;       // n_pad >= i0 + SITE_TILE: no bounds check
         const double* tb = v.theta + (size_t)t4 * Cp + cw + g;
         const int ksteps = (v.pq + 3) >> 2;
-#pragma unroll 2
+#pragma unroll 4
         for (int ks = 0; ks < ksteps; ks++) {
             const double a = ua[(size_t)ks * 4 * v.n_pad];
             double b[4];
