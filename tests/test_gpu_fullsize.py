@@ -123,3 +123,32 @@ def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains):
         np.testing.assert_allclose(out2['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
         np.testing.assert_allclose(out2['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
     eng.close()
+
+
+def test_device_moran_basis_is_an_eigenbasis():
+    """Large RSR bases (q > 256 beyond the dense-host limit) come from a dense FP64 eigh on the device
+    (gibbs/_setup.py:_device_moran_eigh; reference: logit.py:417-447).  The returned columns are orthonormal
+    eigenvectors of the Moran operator n P A P / 1'A1 with the q largest eigenvalues, ascending."""
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.gibbs import _setup
+    Q, W, X, y, *_ = make_data(n=3500, min_v=2, max_v=4, lattice=(50, 70), random_state=2)
+    q = 300
+    K = _setup.rsr_basis(Q, X, q=q)
+    assert K.shape == (3500, q)
+    op, A, XtX_inv = _setup.moran_operator(Q, X)
+    OK = op.matmat(K)
+    lam = np.einsum('ij,ij->j', K, OK)
+    np.testing.assert_allclose(K.T @ K, np.eye(q), atol=1e-10)
+    assert np.max(np.linalg.norm(OK - K * lam, axis=0)) < 1e-9 * max(1.0, np.abs(lam).max())
+    assert np.all(np.diff(lam) > -1e-9)
+    # nothing outside the span has a larger eigenvalue than the smallest one kept: power iteration on the deflated operator
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=3500)
+    for _ in range(200):
+        v -= K @ (K.T @ v)
+        v = op.matvec(v).ravel()
+        v /= np.linalg.norm(v)
+    v -= K @ (K.T @ v)
+    v /= np.linalg.norm(v)
+    top_outside = float(v @ op.matvec(v).ravel())
+    assert top_outside <= lam[0] + 1e-6
