@@ -12,7 +12,7 @@
 //     Z[:, m] / c_m   = sum_{t=1..SB} b_t 256^-t,   b_t in [-128, 127]  (balanced signed digits of
 //                       rint(Z / c_m 2^(8 SB)), |Z / c_m| <= 0.495, c_m a power of two)
 //     G[c][m]         = 8 c_m  sum_{L = s + t <= LMAX} 256^-L  sum_i a_s[i][c] b_t[i][m]
-// Every inner sum is a u8 x s8/u8 -> s32 tensor-core product: exact and order-independent.  One CTA owns a
+// Every inner sum is a u8 x s8 -> s32 tensor-core product: exact and order-independent.  One CTA owns a
 // 128-chain x BN-column tile; the NLEV = LMAX - 1 levels are NLEV accumulators side by side in TMEM
 // (NLEV x BN <= 512 columns), so a stage of operands (SA omega slices + SB Z slices of one 64-byte K block) feeds
 // all NPAIR slice pairs: 2.7x more MMA work per staged byte than a plain GEMM tile.
@@ -21,17 +21,19 @@
 // tensor-pipe cycles: 166 B/clk against the 128 B/clk the pipe can read -- measured: 72 % smem pipe, 55 % tensor
 // pipe).  The slices of Z are therefore stored t-major, [t][BN rows], so that the accumulators of CONSECUTIVE
 // levels s + 1, s + 2, ... are the product of ONE omega slice s with SEVERAL consecutive Z slices: one wide MMA
-// (N up to 256) replaces three or four and reads the omega tile once (110 B/clk).  Only the first K block of a
+// (N up to 256) replaces three or four and reads the omega tile once (112 B/clk; measured: tensor pipe 76 %).  Only the first K block of a
 // work item, where some accumulators of such a run start from zero and others do not, is issued pair by pair.
 //
-// K is cut into chunks short enough that no INT32 accumulator can overflow (5 pairs x 255 x 128 per site and
-// level => 13120 sites); a work item is (tile, chunk).  With one chunk the epilogue writes G and H directly,
+// K is cut into chunks short enough that no INT32 accumulator can overflow (at most 6 pairs x 255 x 128 per site
+// and level => 10944 sites); a work item is (tile, chunk).  With one chunk the epilogue writes G and H directly,
 // otherwise each chunk writes its own partial and a fixed-order reduction follows.  The FP64 recombination
 // (sum_L 256^-L C_L, scaling by 8 c_m) happens in the epilogue straight from TMEM; no INT32 ever reaches HBM.
+// The Z planes are never stored in FP64: they are sliced once from U' (slice_rows_from_ut_kernel); the omega / z
+// planes are written by the site pass every iteration.
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over work items):
 //   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_64B boxes, 3-stage mbarrier ring)
-//   warp 1    MMA issuer    (one elected lane: 2 x NPAIR tcgen05.mma per stage, tcgen05.commit frees the stage)
+//   warp 1    MMA issuer    (one elected lane: 16 wide tcgen05.mma per stage, tcgen05.commit frees the stage)
 //   warps 2-5 epilogue      (tcgen05.ld 32x32b.x16 per level -> FP64 -> global)
 #pragma once
 #include <cuda.h>
