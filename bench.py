@@ -179,6 +179,17 @@ def fp64_peak_tflops(torch):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+_JSON_FD = None
+
+
+def _emit(text):
+    if _JSON_FD is None:
+        print(text, flush=True)
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, (text + '\n').encode())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -187,9 +198,12 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION prints a banner on stdout, which must carry exactly one JSON line
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # stdout must carry exactly one JSON line, and NCCL prints its version banner there from native code: everything
+        # written to fd 1 during the run goes to stderr, the JSON line goes to the saved descriptor at the end
+        global _JSON_FD
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from occuspytial_b200 import LogitRSRGibbs, _lib
     from occuspytial_b200.gibbs.parallel import allgather_summaries
@@ -379,7 +393,7 @@ def run_b200(args):
         line['cpu_baseline'] = {'value': v, 'unit': 'chain-iterations/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{cores} chains x {args.cpu_iters} iterations of the same workload, one '
                                           f'process per chain, {el:.1f} s (oracle/sweep.py + oracle/pg_devroye.c)'}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
