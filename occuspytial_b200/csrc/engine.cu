@@ -137,6 +137,7 @@ struct occu_engine {
     size_t ws_bytes;
     gtc::Geometry geo;
     int sm_count;
+    size_t smem_configured[3];  // dynamic shared memory already opted in for the ICAR / RSR / tiled solve kernels
     int tc_order;           // tile order of the tcgen05 Gram (gtc::Params::order; OCCU_TC_ORDER overrides)
     CUtensorMap tmA, tmB;
     bool slices_valid;      // Aq holds the digits of the current (omega, z)
@@ -2813,7 +2814,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     PROF_MARK(e, KC_SOLVE, st);
     if (v.model == OCCU_LOGIT_ICAR) {
         const size_t smem_i = icar_smem_bytes(v);
-        static size_t configured_i = 0;
+        size_t& configured_i = e->smem_configured[0];   // per engine: the attribute is per device
         if (smem_i > configured_i) {
             CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
             configured_i = smem_i;
@@ -2831,14 +2832,14 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         return 0;
     }
     const size_t smem = v.solve_stride ? 0 : solve_smem_bytes(v);
-    static size_t configured = 0;
+    size_t& configured = e->smem_configured[1];
     if (smem > configured) {
         CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     if (v.solve_stride) {   // large q: tiled factorisation out of global scratch
         const size_t smem_t = tiled_smem_bytes(v.q, v.pq);
-        static size_t configured_t = 0;
+        size_t& configured_t = e->smem_configured[2];
         if (smem_t > configured_t) {
             CUDA_OK(cudaFuncSetAttribute(solve_logit_rsr_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
             configured_t = smem_t;
@@ -2900,6 +2901,7 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
         const char* ord = getenv("OCCU_TC_ORDER");
         e->tc_order = ord ? atoi(ord) : 0;
+        e->smem_configured[0] = e->smem_configured[1] = e->smem_configured[2] = 0;
     }
     for (int k = 0; k < KC_COUNT; k++) { e->kernel_ms[k] = 0.0; e->kernel_calls[k] = 0; }
     for (int k = 0; k <= KC_COUNT; k++) e->ev[k] = nullptr;
