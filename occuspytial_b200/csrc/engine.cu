@@ -2143,7 +2143,9 @@ __global__ void __launch_bounds__(ICAR_THREADS) solve_logit_icar_kernel(const Vi
 // already-known x in parallel, one lane finishes the 4x4 triangular solve; L is prefetched one block ahead.
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(128, 5) solve_logit_icar_mma_kernel(const View v, const SolveDebug dbg, double* rec_beta,
+// 7 resident CTAs per SM (72 registers, < 32 KB of shared memory): 1036 chain slots on 148 SMs, so that the 1024 chains
+// of BASELINE config 4 are one wave instead of 1.4 (measured 7.7 -> 6.6 ms per iteration); the widest bands keep 5
+__global__ void __launch_bounds__(128, NT <= 7 ? 7 : 5) solve_logit_icar_mma_kernel(const View v, const SolveDebug dbg, double* rec_beta,
                                                                     double* rec_tau, int rec_capacity) {
     constexpr int W8 = 8 * NT, T = 128, RPW = (NT + 1 + 3) / 4;  // tile rows per warp (incl. the RHS tile row NT)
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -2155,7 +2157,7 @@ __global__ void __launch_bounds__(128, 5) solve_logit_icar_mma_kernel(const View
     __shared__ double P[W8 + 8][4];
     __shared__ double xr[3][W8];          // rings of the backward solves
     __shared__ double S4[4][3];           // backward: the four column sums of a block
-    constexpr int NBF = 4, NBB = 8;       // prefetch depth (block steps) of the forward / backward pass
+    constexpr int NBF = 2, NBB = 4;       // prefetch depth (block steps) of the forward / backward pass
     __shared__ double qin[NBF][4][64];    // ring: lower-band rows of Q for the 4 matrix rows entering at a block step
     __shared__ double oin[NBF][4], bin[NBF][4];  // their omega and b
     __shared__ double lring[NBB][4][64];  // backward ring: the 4 columns of L of a block (column-band layout)
