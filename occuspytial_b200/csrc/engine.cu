@@ -930,7 +930,7 @@ __device__ __forceinline__ bool chol4(double (&a)[4][4], double (&invd)[4]) {
     return true;
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
+__global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
                                                                          double* rec_alpha, double* rec_beta,
                                                                          double* rec_tau, int rec_capacity) {
     extern __shared__ double sm_dyn[];
