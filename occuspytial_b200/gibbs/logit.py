@@ -1,7 +1,7 @@
 """Logit-link samplers: LogitICARGibbs (alias PGGibbs) and LogitRSRGibbs.
 
 API of occuspytial/gibbs/logit.py:102-485; the sweep itself (``step``: omega_b, tau, eta, beta, omega_a,
-alpha, z -- logit.py:254-266) runs in the CUDA engine, see occuspytial_b200/csrc/engine.cu.
+alpha, z -- logit.py:254-266) runs in the CUDA engine, see occuspytial_b200/csrc/ (engine.cu and the headers it includes).
 """
 import numpy as np
 
