@@ -48,7 +48,9 @@ static bool fuse_psi(const occu_engine* e) {
         const char* s = getenv("OCCU_FUSE_PSI");
         allowed = s ? atoi(s) : 1;
     }
-    return allowed && e->v.model == OCCU_LOGIT_RSR && !e->pg_fp64;
+    // beyond ~128 columns of [X K] the in-pass DMMA product (no operand reuse across the 8-site sub-tiles) costs more
+    // than the tiled GEMM plus the psi round trip (measured at q = 1256: 2.7 vs 1.3 ms per 1024 chains)
+    return allowed && e->v.model == OCCU_LOGIT_RSR && !e->pg_fp64 && e->v.pq <= 128;
 }
 
 template <typename PGT, bool SLICES, bool FUSE_PSI>
