@@ -351,7 +351,7 @@ def run_b200(args):
                     'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
     site_ms, site_calls = kms['site_pass']
     # psi in (unless fused), z in/out, then omega + kd out (FP64 Gram path) or the 7 byte planes of (omega, z)
-    fused_psi = not args.pg_fp64 and os.environ.get('OCCU_FUSE_PSI', '1') != '0'   # psi formed inside the site pass
+    fused_psi = not args.pg_fp64 and os.environ.get('OCCU_FUSE_PSI', '1') != '0' and pq <= 128   # psi formed inside the site pass
     site_bytes_alg = ((0 if fused_psi else 8) + 2 + (7 if gram_path == 'int8' else 16)) * wl['n'] * args.chains
     line = {
         'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': world, 'steps': args.steps,
