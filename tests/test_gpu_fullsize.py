@@ -71,7 +71,9 @@ def test_full_size_sharding_and_determinism(big):
 
 
 @pytest.mark.parametrize('shape,q,chains', [((100, 100), 64, 3),     # headline shape: one K chunk, G written directly
-                                             ((100, 120), 12, 5)])    # n = 12000: two K chunks + fixed-order reduction
+                                             ((100, 120), 12, 5),     # n = 12000: two K chunks + fixed-order reduction
+                                             ((33, 34), 33, 200),     # ragged everything: n = 1122, 2 chain tiles (one partial)
+                                             ((37, 57), 100, 129)])   # n = 2109, 5253 Gram columns, 129 chains
 def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains):
     """The Omega-weighted Gram of the tcgen05 kind::i8 path (csrc/gram_tc.cuh) at sizes the small parity cases do
     not reach: every Gaussian system built from it agrees with a NumPy FP64 evaluation to 1e-10
