@@ -375,7 +375,7 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         const gtc::Geometry& g = e->geo;
         gtc::slice_rows_from_ut_kernel<<<g.Mrows, 256, 0, st>>>(v.UT, v.n, v.n_pad, g.Kp, v.M, g.Mg_pad, v.pq, g.Mrows, v.tscale,
                                                                  v.Bq);
-        gtc::hshift_from_ut_kernel<<<(v.ldh + 127) / 128, 128, 0, st>>>(v.UT, v.n, v.n_pad, v.pq, v.ldh, v.hshift);
+        gtc::hshift_from_ut_kernel<<<v.ldh, 128, 0, st>>>(v.UT, v.n, v.n_pad, v.pq, v.ldh, v.hshift);
         e->launches += 2;
         FAIL_IF(cudaMemsetAsync(v.Aq, 0, (size_t)(gtc::SA + 1) * v.Cp * g.Kp, st));
         FAIL_IF(cudaMemsetAsync(v.G, 0, (size_t)v.Cp * v.M_pad * 8, st));

@@ -646,14 +646,23 @@ __global__ void __launch_bounds__(256) slice_rows_from_ut_kernel(const double* _
     }
 }
 
-// hshift[a] = -1/2 sum_i U[i][a] (fixed order) from the rows of UT
-__global__ void hshift_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int pq, int ldh, double* __restrict__ hshift) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+// hshift[a] = -1/2 sum_i U[i][a] from the rows of UT: one CTA per column, strided partial sums combined by a fixed
+// tree (deterministic)
+__global__ void __launch_bounds__(128) hshift_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int pq, int ldh,
+                                                              double* __restrict__ hshift) {
+    __shared__ double part[128];
+    const int a = blockIdx.x, tid = threadIdx.x;
     if (a >= ldh) return;
     double acc = 0.0;
     if (a < pq)
-        for (int i = 0; i < n; i++) acc += UT[(size_t)a * ldu + i];
-    hshift[a] = -0.5 * acc;
+        for (int i = tid; i < n; i += 128) acc += UT[(size_t)a * ldu + i];
+    part[tid] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o) part[tid] += part[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) hshift[a] = -0.5 * part[0];
 }
 
 // Aq[s][c][i] = digit s+1 of floor(omega[i][c] 2^45) (48-bit fixed point of omega / 8), Aq[Z_SLICE][c][i] = z[i][c].
