@@ -8,7 +8,7 @@ Q, W, X, y, *_ = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random
 K = _setup.rsr_basis(Q, X, q=64)
 s = LogitRSRGibbs(Q, W, X, y, random_state=10, K=K)
 C = 4096
-for splits in (1, 2):
+for splits in (1, 2, 4):
     per = C // splits
     start = s._start_arrays(C, None)
     engs = []
