@@ -70,11 +70,13 @@ def test_full_size_sharding_and_determinism(big):
         np.testing.assert_array_equal(out[0][k], out[2][k])
 
 
-@pytest.mark.parametrize('shape,q,chains', [((100, 100), 64, 3),     # headline shape: one K chunk, G written directly
-                                             ((100, 120), 12, 5),     # n = 12000: two K chunks + fixed-order reduction
-                                             ((33, 34), 33, 200),     # ragged everything: n = 1122, 2 chain tiles (one partial)
-                                             ((37, 57), 100, 129)])   # n = 2109, 5253 Gram columns, 129 chains
-def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains):
+@pytest.mark.parametrize('shape,q,chains,p,r', [
+    ((100, 100), 64, 3, 3, 3),     # headline shape: one K chunk, G written directly
+    ((100, 120), 12, 5, 3, 3),     # n = 12000: two K chunks + fixed-order reduction
+    ((33, 34), 33, 200, 3, 3),     # ragged everything: n = 1122, 2 chain tiles (one partial)
+    ((37, 57), 100, 129, 3, 3),    # n = 2109, 5253 Gram columns, 129 chains
+    ((32, 40), 17, 70, 5, 2)])     # other covariate counts (p = 5, r = 2): other template instances, pq = 22
+def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains, p, r):
     """The Omega-weighted Gram of the tcgen05 kind::i8 path (csrc/gram_tc.cuh) at sizes the small parity cases do
     not reach: every Gaussian system built from it agrees with a NumPy FP64 evaluation to 1e-10
     (reference: logit.py:226-232, 325-337, 478-485)."""
@@ -83,12 +85,12 @@ def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains):
     from occuspytial_b200.gibbs import _setup
     from oracle import sweep as S
     n = shape[0] * shape[1]
-    Q, W, X, y, *_ = make_data(n=n, min_v=2, max_v=6, lattice=shape, random_state=1)
+    Q, W, X, y, *_ = make_data(n=n, min_v=2, max_v=6, lattice=shape, p=p, q=r, random_state=1)
     K = _setup.rsr_basis(Q, X, q=q)
     s = LogitRSRGibbs(Q, W, X, y, random_state=4, K=K)
     f = s.fixed
     prob = s._problem_arrays()
-    V, r, p = prob['W_rows'].shape[0], 3, 3
+    V = prob['W_rows'].shape[0]
     rng = np.random.default_rng(8)
     eng = s._make_engine(chains, seed=3, debug=True)     # n >= 1024: the tcgen05 path is the default
     assert eng.gram_int8
