@@ -135,7 +135,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
