@@ -322,9 +322,10 @@ def run_b200(args):
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     total_ms = sum(v[0] / max(v[1], 1) for v in kms.values())
     if gram_path == 'int8':
-        # gram_tc_kernel (csrc/gram_tc.cuh): 21 slice pairs (6 omega x 6 Z slices, levels s + t <= 7) over 128-chain x
+        # gram_tc_kernel (csrc/gram_tc.cuh): slice pairs (omega planes x 6 Z planes, levels s + t <= 7) over 128-chain x
         # 64-column tiles, plus the 6 slices of the U'z tiles
-        PAIRS, SB = 21, 6
+        # production precision: omega is a 32-bit fixed-point number (4 byte planes) -> 18 slice pairs; FP64 draws: 21
+        PAIRS, SB = (21 if args.pg_fp64 else 18), 6
         # useful INT8 operations of the slicing algorithm (no tile / K padding counted): PAIRS products of the
         # [chains x n] omega planes with the [n x M] Z planes, SB products of the z plane with the [n x pq] U planes
         int8_ops = 2.0 * args.chains * wl['n'] * (M * PAIRS + pq * SB)
@@ -352,7 +353,7 @@ def run_b200(args):
     site_ms, site_calls = kms['site_pass']
     # psi in (unless fused), z in/out, then omega + kd out (FP64 Gram path) or the 7 byte planes of (omega, z)
     fused_psi = not args.pg_fp64 and os.environ.get('OCCU_FUSE_PSI', '1') != '0' and pq <= 128   # psi formed inside the site pass
-    site_bytes_alg = ((0 if fused_psi else 8) + 2 + (7 if gram_path == 'int8' else 16)) * wl['n'] * args.chains
+    site_bytes_alg = ((0 if fused_psi else 8) + 2 + ((7 if args.pg_fp64 else 5) if gram_path == 'int8' else 16)) * wl['n'] * args.chains
     line = {
         'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

@@ -41,13 +41,14 @@ __global__ void fill_zu(double* ZU, int n, int ld, int M, int src_u0, int pq) {
     }
     ZU[idx] = v;
 }
-__global__ void fill_omega(double* om, uint8_t* z, size_t count) {
+__global__ void fill_omega(double* om, uint8_t* z, size_t count, int planes) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
     const double u = u01(idx + 0xABCDEFull);
     double w = 0.25 * exp(3.0 * (u01(idx * 3 + 7) - 0.7));  // ~ PG(1, c) magnitudes, 0.03 .. 0.6
     if (u < 1e-4) w = 7.9999;                               // near the saturation bound
     if (u > 1.0 - 1e-4) w = 1e-9;
+    if (planes == gtc::SA_F32) w = rint(w * 536870912.0) * (1.0 / 536870912.0);   // 32-bit fixed point of omega / 8
     om[idx] = w;
     z[idx] = u01(idx * 5 + 11) < 0.4 ? 1 : 0;
 }
@@ -143,7 +144,8 @@ int run(int n, int C, int pq, int want_split) {
     CK(cudaMemset(Gpart, 0xFF, g.nsplit * gstride * 8));
 
     fill_zu<<<(unsigned)(((size_t)n * ld + 255) / 256), 256>>>(ZU, n, ld, M, src_u0, pq);
-    fill_omega<<<(unsigned)(((size_t)n * Cp + 255) / 256), 256>>>(omega, z, (size_t)n * Cp);
+    const int planes = getenv("SAV") ? atoi(getenv("SAV")) : gtc::SA;   // 4: omega on the 32-bit grid, kernel skips planes 5, 6
+    fill_omega<<<(unsigned)(((size_t)n * Cp + 255) / 256), 256>>>(omega, z, (size_t)n * Cp, planes);
     gtc::column_scale_kernel<<<(ld + 127) / 128, 128>>>(ZU, n, ld, ld, cscale);
     gtc::slice_b_kernel<<<dim3((g.Kp + 255) / 256, g.Mrows), 256>>>(ZU, n, g.Kp, ld, M, g.Mg_pad, pq, src_u0, g.Mrows, cscale, scale,
                                                                     Bq);
@@ -166,12 +168,14 @@ int run(int n, int C, int pq, int want_split) {
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaFuncSetAttribute(gtc::gram_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::Cfg<BN>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gtc::gram_tc_kernel<BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::Cfg<BN>::SMEM_BYTES));
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
     const int grid = nitems < sms ? nitems : sms;
 
     auto step = [&]() {
         gtc::slice_a_kernel<<<dim3((g.Kp + 31) / 32, Cp / 32), 256>>>(omega, z, n, g.Kp, Cp, Aq);
-        gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+        else gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
         gtc::reduce_parts_kernel<<<(unsigned)((gstride + 255) / 256), 256>>>(Gpart, g.nsplit, gstride, gstride, M64, M, G);
         gtc::reduce_parts_kernel<<<(unsigned)((hstride + 255) / 256), 256>>>(Hpart, g.nsplit, hstride, hstride, pq64, pq, H);
     };
@@ -238,7 +242,10 @@ int run(int n, int C, int pq, int want_split) {
     const int reps = 20;
     for (int w = 0; w < 3; w++) step();
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; r++) gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+    for (int r = 0; r < reps; r++) {
+        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+        else gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+    }
     cudaEventRecord(e1e);
     CK(cudaDeviceSynchronize());
     float ms_k = 0, ms_s = 0;
@@ -248,7 +255,10 @@ int run(int n, int C, int pq, int want_split) {
     cudaEventRecord(e1e);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms_s, e0, e1e);
-    const double macs = (double)Cp * g.Kp * ((double)g.n_gt * BN * gtc::NPAIR + (double)g.n_ht * BN * gtc::SB);
+    int pairs = 0;   // slice pairs issued: s <= planes, t <= SB, s + t <= LMAX
+    for (int s_ = 1; s_ <= planes; s_++)
+        for (int t_ = 1; t_ <= gtc::SB; t_++) pairs += (s_ + t_ <= gtc::LMAX);
+    const double macs = (double)Cp * g.Kp * ((double)g.n_gt * BN * pairs + (double)g.n_ht * BN * gtc::SB);
     printf("time     : gram kernel %.3f ms (%.2f int8 POP/s issued), slice + gram + reduce %.3f ms; grid %d, items %d\n", ms_k / reps,
            2.0 * macs / (ms_k / reps * 1e-3) / 1e15, ms_s / reps, grid, nitems);
     for (int mode = 1; mode <= 2; mode++) {  // bottleneck probes

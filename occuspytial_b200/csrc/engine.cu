@@ -87,11 +87,17 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
         e->launches++;
     } else if (v.int8) {
         // the site pass writes the digits of (omega, z) for the tcgen05 Gram itself
+        if (!e->pg_fp64 && e->low_planes_dirty) {   // an injected 48-bit omega was sliced earlier: clear its low planes
+            const size_t plane = (size_t)v.Cp * v.tc_Kp;
+            cudaMemsetAsync(v.Aq + (size_t)gtc::SA_F32 * plane, 0, (size_t)(gtc::SA - gtc::SA_F32) * plane, st);
+            e->low_planes_dirty = false;
+        }
         if (e->pg_fp64) launch_site_pass_logit<double, true, false>(e, st);
         else if (fuse_psi(e)) launch_site_pass_logit<float, true, true>(e, st);
         else launch_site_pass_logit<float, true, false>(e, st);
         e->slices_valid = true;
         e->omega_in_slices = v.zprob == nullptr;
+        e->omega_planes = e->pg_fp64 ? gtc::SA : gtc::SA_F32;
     } else if (e->pg_fp64) {
         launch_site_pass_logit<double, false, false>(e, st);
     } else if (fuse_psi(e)) {
@@ -141,6 +147,8 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
         e->launches++;
         e->slices_valid = true;
         e->omega_in_slices = false;
+        e->omega_planes = gtc::SA;
+        e->low_planes_dirty = true;
     }
     gtc::Params p;
     p.Cp = v.Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
@@ -151,7 +159,10 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     p.Hpart = g.nsplit > 1 ? v.Hp : v.Hpart;
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
     const int grid = nitems < e->sm_count ? nitems : e->sm_count;
-    gtc::gram_tc_kernel<TC_BN><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+    if (e->omega_planes == gtc::SA_F32)
+        gtc::gram_tc_kernel<TC_BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+    else
+        gtc::gram_tc_kernel<TC_BN, gtc::SA><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
     e->launches++;
     if (g.nsplit > 1) {
         const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
@@ -369,6 +380,8 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     }
     e->slices_valid = false;
     e->omega_in_slices = false;
+    e->omega_planes = gtc::SA;
+    e->low_planes_dirty = false;
     if (v.int8) {
         // slice [Z | U] once (formed on the fly from U'), encode the TMA descriptors of the two operand arrays
         e->geo = gtc::make_geometry(v.n, v.Cp, v.M, v.pq, TC_BN);
@@ -382,8 +395,10 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         FAIL_IF(cudaMemsetAsync(v.tc_err, 0, sizeof(int), st));
         const char* why = gtc::make_map(&e->tmA, v.Aq, (uint64_t)(gtc::SA + 1) * v.Cp, g.Kp, gtc::BM);
         if (!why) why = gtc::make_map(&e->tmB, v.Bq, (uint64_t)gtc::SB * g.Mrows, g.Kp, TC_BN);
-        if (!why && cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess)
+        if (!why && (cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess ||
+                     cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess))
             why = "cudaFuncSetAttribute(shared memory) failed";
         if (why) {
             occu_destroy(e);

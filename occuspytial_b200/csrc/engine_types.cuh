@@ -114,6 +114,8 @@ struct occu_engine {
     int tc_order;           // tile order of the tcgen05 Gram (gtc::Params::order; OCCU_TC_ORDER overrides)
     CUtensorMap tmA, tmB;
     bool slices_valid;      // Aq holds the digits of the current (omega, z)
+    int omega_planes;       // omega byte planes that can be non-zero: SA_F32 after a production (FP32) site pass, else SA
+    bool low_planes_dirty;  // planes SA_F32 .. SA - 1 hold digits of an older 48-bit omega
     bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines)
     int profiling;
     double kernel_ms[KC_COUNT];

@@ -29,7 +29,9 @@
 // otherwise each chunk writes its own partial and a fixed-order reduction follows.  The FP64 recombination
 // (sum_L 256^-L C_L, scaling by 8 c_m) happens in the epilogue straight from TMEM; no INT32 ever reaches HBM.
 // The Z planes are never stored in FP64: they are sliced once from U' (slice_rows_from_ut_kernel); the omega / z
-// planes are written by the site pass every iteration.
+// planes are written by the site pass every iteration.  In production precision omega is drawn in FP32 and stored as
+// a 32-bit fixed-point number (exact for omega >= 2^-6, rounded to 2^-29 below): only SA_F32 = 4 planes can be
+// non-zero and the kernel is instantiated without the pairs of the other two (18 instead of 21).
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over work items):
 //   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_64B boxes, 3-stage mbarrier ring)
@@ -46,6 +48,7 @@ namespace gtc {
 #define GTC_SB 6
 #endif
 constexpr int SA = 6;             // omega slices (unsigned bytes): 48-bit fixed point of omega / 8
+constexpr int SA_F32 = 4;         // ... of which the first 4 can be non-zero when omega was drawn in FP32 (32-bit fixed point)
 constexpr int SB = GTC_SB;        // Z slices (balanced signed bytes): 6 -> |error| <= 2^-49 c_m per entry, 5 -> 2^-41 c_m
 constexpr int LMAX = 7;           // keep slice pairs with s + t <= LMAX (dropped products are below 2^-56 of the scale)
 constexpr int NLEV = LMAX - 1;    // levels 2 .. LMAX
@@ -205,21 +208,24 @@ __device__ __forceinline__ void issue_one_g(uint32_t tmem_base, uint32_t a_lo, u
     constexpr bool start = FIRST && K2 == 0 && first_of_level(S, T);
     mma_i8_imm<!start>(tmem_base + lev * BN, desc_from(a_lo + aoff), desc_from(b_lo + boff), id);
 }
-template <int BN, bool FIRST, int S, int T>
+// SAV = number of omega planes that can be non-zero (SA, or 4 when the site pass wrote 32-bit fixed-point omega):
+// the pairs of the planes beyond it are not issued.  (The first pair of every level has s = 1, so first_of_level
+// does not depend on SAV.)
+template <int BN, int SAV, bool FIRST, int S, int T>
 __device__ __forceinline__ void issue_pairs_g(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
-    if constexpr (S <= SA) {
+    if constexpr (S <= SAV) {
         if constexpr (S + T <= LMAX && T <= SB) {
             issue_one_g<BN, S, T, 0, FIRST>(tmem_base, a_lo, b_lo);
             issue_one_g<BN, S, T, 1, FIRST>(tmem_base, a_lo, b_lo);
         }
-        if constexpr (T < SB) issue_pairs_g<BN, FIRST, S, T + 1>(tmem_base, a_lo, b_lo);
-        else issue_pairs_g<BN, FIRST, S + 1, 1>(tmem_base, a_lo, b_lo);
+        if constexpr (T < SB) issue_pairs_g<BN, SAV, FIRST, S, T + 1>(tmem_base, a_lo, b_lo);
+        else issue_pairs_g<BN, SAV, FIRST, S + 1, 1>(tmem_base, a_lo, b_lo);
     }
 }
-template <int BN, bool FIRST>
+template <int BN, int SAV, bool FIRST>
 __device__ __forceinline__ void issue_g(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
     static_assert(BK == 64, "two K = 32 MMAs per stage");
-    issue_pairs_g<BN, FIRST, 1, 1>(tmem_base, a_lo, b_lo);
+    issue_pairs_g<BN, SAV, FIRST, 1, 1>(tmem_base, a_lo, b_lo);
 }
 template <int BN, bool FIRST, int T>
 __device__ __forceinline__ void issue_pairs_h(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
@@ -252,17 +258,17 @@ __device__ __forceinline__ void issue_run(uint32_t tmem_base, uint32_t a_lo, uin
         issue_run<BN, S, T0 + nb, TMAX, K2, LEV0>(tmem_base, a_lo, b_lo);
     }
 }
-template <int BN, int S, int K2>
+template <int BN, int SAV, int S, int K2>
 __device__ __forceinline__ void issue_slices_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
-    if constexpr (S <= SA) {
+    if constexpr (S <= SAV) {
         issue_run<BN, S, 1, imin(SB, LMAX - S), K2, S - 1>(tmem_base, a_lo, b_lo);  // level index of (S, 1) is S - 1
-        issue_slices_wide<BN, S + 1, K2>(tmem_base, a_lo, b_lo);
+        issue_slices_wide<BN, SAV, S + 1, K2>(tmem_base, a_lo, b_lo);
     }
 }
-template <int BN>
+template <int BN, int SAV>
 __device__ __forceinline__ void issue_g_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
-    issue_slices_wide<BN, 1, 0>(tmem_base, a_lo, b_lo);
-    issue_slices_wide<BN, 1, 1>(tmem_base, a_lo, b_lo);
+    issue_slices_wide<BN, SAV, 1, 0>(tmem_base, a_lo, b_lo);
+    issue_slices_wide<BN, SAV, 1, 1>(tmem_base, a_lo, b_lo);
 }
 template <int BN>
 __device__ __forceinline__ void issue_h_wide(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo) {
@@ -362,10 +368,10 @@ struct Sched {
     }
 };
 
-template <int BN>
 #ifndef GTC_MIN_BLOCKS
 #define GTC_MIN_BLOCKS 1
 #endif
+template <int BN, int SAV = SA>
 __global__ void __launch_bounds__(THREADS, GTC_MIN_BLOCKS)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     using C = Cfg<BN>;
@@ -410,7 +416,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (sched.next(p, it)) {
                 const int arow = it.mt * BM;
                 const int brow = it.nt * BN;
-                const uint32_t bytes = (it.is_h ? A_TILE_BYTES : SA * A_TILE_BYTES) + SB * C::B_TILE_BYTES;
+                const uint32_t bytes = (it.is_h ? A_TILE_BYTES : SAV * A_TILE_BYTES) + SB * C::B_TILE_BYTES;
                 for (int kb = it.kb0; kb < it.kb1; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -428,7 +434,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(&tmA, &full[stage], sa, kb * BK, Z_SLICE * p.Cp + arow);
                     } else {
 #pragma unroll
-                        for (int s = 0; s < SA; s++)
+                        for (int s = 0; s < SAV; s++)
                             tma_load_2d(&tmA, &full[stage], sa + s * A_TILE_BYTES, kb * BK, s * p.Cp + arow);
                     }
 #pragma unroll
@@ -464,8 +470,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (kb == it.kb0) issue_h<BN, true>(tmem_base, a_lo, b_lo);
                         else issue_h_wide<BN>(tmem_base, a_lo, b_lo);
                     } else {
-                        if (kb == it.kb0) issue_g<BN, true>(tmem_base, a_lo, b_lo);
-                        else issue_g_wide<BN>(tmem_base, a_lo, b_lo);
+                        if (kb == it.kb0) issue_g<BN, SAV, true>(tmem_base, a_lo, b_lo);
+                        else issue_g_wide<BN, SAV>(tmem_base, a_lo, b_lo);
                     }
                     tc_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
                     if (++stage == STAGES) {

@@ -194,35 +194,49 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
     }
 
     // ---- phase 3: write-out ----
-    if (!SLICES || v.zprob)
+    if (!SLICES)
         for (int ii = i0; ii < i1; ii++) v.omega[(size_t)ii * Cp + c] = (double)arg_s[ii - i0][tid];
     if (SLICES) {
+        // omega as a fixed-point number of omega / 8.  FP32 draws (production): 32 bits -- exact for every omega >=
+        // 2^-6 (a float has 24 significant bits), rounded to 2^-29 below that, which is the resolution the FP32
+        // arithmetic of the draw has anyway; only the first NPL = 4 byte planes are written and the Gram kernel skips
+        // the pairs of the two empty ones.  FP64 draws (validation build): all 48 bits.  omega IS that fixed-point
+        // value: a debug engine's FP64 copy is written from it.
+        constexpr int NPL = std::is_same<PGT, float>::value ? gtc::SA_F32 : gtc::SA;
         static_assert(SITE_TILE % 16 == 0, "16 sites per 128-bit store");
         const size_t plane = (size_t)Cp * v.tc_Kp;
         uint8_t* row = v.Aq + (size_t)c * v.tc_Kp + i0;
 #pragma unroll 1
         for (int g = 0; g < SITE_TILE / 16; g++) {
-            uint32_t w[gtc::SA + 1][4];
+            uint32_t w[NPL + 1][4];
 #pragma unroll
-            for (int s = 0; s <= gtc::SA; s++)
+            for (int s = 0; s <= NPL; s++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) w[s][k] = 0u;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const int ii = g * 16 + j;
-                unsigned long long q = 0ull;
+                unsigned long long q = 0ull;   // (omega / 8) 2^48
                 if (i0 + ii < i1) {
-                    const double x = (double)arg_s[ii][tid] * 35184372088832.0;  // omega 2^45 = (omega / 8) 2^48
-                    q = x >= 281474976710655.0 ? 281474976710655ull : (x > 0.0 ? (unsigned long long)x : 0ull);
+                    if (NPL == gtc::SA) {
+                        const double x = (double)arg_s[ii][tid] * 35184372088832.0;   // 2^45
+                        q = x >= 281474976710655.0 ? 281474976710655ull : (x > 0.0 ? (unsigned long long)x : 0ull);
+                    } else {
+                        const double x = rint((double)arg_s[ii][tid] * 536870912.0);   // 2^29, round to nearest
+                        q = (x >= 4294967295.0 ? 4294967295ull : (x > 0.0 ? (unsigned long long)x : 0ull)) << 16;
+                    }
+                    if (v.zprob) v.omega[(size_t)(i0 + ii) * Cp + c] = (double)q * (1.0 / 35184372088832.0);
                 }
                 const int sh = 8 * (j & 3);
 #pragma unroll
-                for (int s = 0; s < gtc::SA; s++) w[s][j >> 2] |= (uint32_t)((q >> (8 * (gtc::SA - 1 - s))) & 0xFFull) << sh;
-                w[gtc::SA][j >> 2] |= (uint32_t)((zbits >> ii) & 1ull) << sh;
+                for (int s = 0; s < NPL; s++) w[s][j >> 2] |= (uint32_t)((q >> (8 * (gtc::SA - 1 - s))) & 0xFFull) << sh;
+                w[NPL][j >> 2] |= (uint32_t)((zbits >> ii) & 1ull) << sh;
             }
 #pragma unroll
-            for (int s = 0; s <= gtc::SA; s++)
+            for (int s = 0; s < NPL; s++)
                 *reinterpret_cast<uint4*>(row + (size_t)s * plane + g * 16) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            *reinterpret_cast<uint4*>(row + (size_t)gtc::Z_SLICE * plane + g * 16) =
+                make_uint4(w[NPL][0], w[NPL][1], w[NPL][2], w[NPL][3]);
         }
     }
 #pragma unroll
