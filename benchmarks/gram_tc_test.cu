@@ -168,13 +168,13 @@ int run(int n, int C, int pq, int want_split) {
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaFuncSetAttribute(gtc::gram_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::Cfg<BN>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gtc::gram_tc_kernel<BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::Cfg<BN>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gtc::gram_tc_kernel<BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::Cfg<BN, gtc::SA_F32>::SMEM_BYTES));
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
     const int grid = nitems < sms ? nitems : sms;
 
     auto step = [&]() {
         gtc::slice_a_kernel<<<dim3((g.Kp + 31) / 32, Cp / 32), 256>>>(omega, z, n, g.Kp, Cp, Aq);
-        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN, gtc::SA_F32>::SMEM_BYTES>>>(tmA, tmB, p);
         else gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
         gtc::reduce_parts_kernel<<<(unsigned)((gstride + 255) / 256), 256>>>(Gpart, g.nsplit, gstride, gstride, M64, M, G);
         gtc::reduce_parts_kernel<<<(unsigned)((hstride + 255) / 256), 256>>>(Hpart, g.nsplit, hstride, hstride, pq64, pq, H);
@@ -243,7 +243,7 @@ int run(int n, int C, int pq, int want_split) {
     for (int w = 0; w < 3; w++) step();
     cudaEventRecord(e0);
     for (int r = 0; r < reps; r++) {
-        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
+        if (planes == gtc::SA_F32) gtc::gram_tc_kernel<BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<BN, gtc::SA_F32>::SMEM_BYTES>>>(tmA, tmB, p);
         else gtc::gram_tc_kernel<BN><<<grid, gtc::THREADS, gtc::Cfg<BN>::SMEM_BYTES>>>(tmA, tmB, p);
     }
     cudaEventRecord(e1e);

@@ -160,9 +160,9 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
     const int grid = nitems < e->sm_count ? nitems : e->sm_count;
     if (e->omega_planes == gtc::SA_F32)
-        gtc::gram_tc_kernel<TC_BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+        gtc::gram_tc_kernel<TC_BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA_F32>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
     else
-        gtc::gram_tc_kernel<TC_BN, gtc::SA><<<grid, gtc::THREADS, gtc::Cfg<TC_BN>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+        gtc::gram_tc_kernel<TC_BN, gtc::SA><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
     e->launches++;
     if (g.nsplit > 1) {
         const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
@@ -398,7 +398,7 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         if (!why && (cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess ||
                      cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess))
+                                          gtc::Cfg<TC_BN, gtc::SA_F32>::SMEM_BYTES) != cudaSuccess))
             why = "cudaFuncSetAttribute(shared memory) failed";
         if (why) {
             occu_destroy(e);

@@ -34,7 +34,7 @@
 // non-zero and the kernel is instantiated without the pairs of the other two (18 instead of 21).
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over work items):
-//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_64B boxes, 3-stage mbarrier ring)
+//   warp 0    TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_64B boxes, 3- or 4-stage mbarrier ring)
 //   warp 1    MMA issuer    (one elected lane: 16 wide tcgen05.mma per stage, tcgen05.commit frees the stage)
 //   warps 2-5 epilogue      (tcgen05.ld 32x32b.x16 per level -> FP64 -> global)
 #pragma once
@@ -58,8 +58,7 @@ constexpr int BN_DEFAULT = SB == 6 ? 64 : 80;  // Z columns per tile: NLEV x BN 
 #ifndef GTC_STAGES
 #define GTC_STAGES 3
 #endif
-constexpr int STAGES = GTC_STAGES;
-constexpr int A_SLOTS = SA;       // slot 0 doubles as the z slice for H tiles
+constexpr int STAGES_MIN = GTC_STAGES;   // stages with all SA omega planes staged; 4 planes leave room for one more
 constexpr int A_TILE_BYTES = BM * BK;
 
 constexpr int THREADS = 192;
@@ -78,14 +77,19 @@ constexpr int NPAIR = npairs();
 __host__ __device__ constexpr int imin3(int a, int b, int c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
 constexpr int MAX_KB_PER_CHUNK = (int)(2147483647LL / (255LL * 128LL * imin3(SA, SB, LMAX - 1)) / 64);
 
-template <int BN>
+template <int BN, int SAV = SA>
 struct Cfg {
     static_assert(BN % 16 == 0 && NLEV * BN <= 512, "accumulators must fit the 512 TMEM columns");
     static constexpr int B_TILE_BYTES = BN * BK;
-    static constexpr int STAGE_BYTES = A_SLOTS * A_TILE_BYTES + SB * B_TILE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int STAGE_BYTES = SAV * A_TILE_BYTES + SB * B_TILE_BYTES;   // A slot 0 doubles as the z plane for H tiles
+    static constexpr int EXTRA = 1024 /* alignment slack */ + 256 /* barriers */;
+    // as many stages as fit the 227 KB a CTA can own, at least STAGES_MIN, at most 4
+    static constexpr int FIT = (227 * 1024 - EXTRA) / STAGE_BYTES;
+    static constexpr int STAGES = FIT < STAGES_MIN ? STAGES_MIN : (FIT > 4 ? 4 : FIT);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA;
     static_assert(SMEM_BYTES <= 227 * 1024, "stages must fit the 227 KB of shared memory a CTA can own");
 };
+
 
 struct Params {
     int Cp;             // padded chains (multiple of 128)
@@ -374,7 +378,8 @@ struct Sched {
 template <int BN, int SAV = SA>
 __global__ void __launch_bounds__(THREADS, GTC_MIN_BLOCKS)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, SAV>;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -420,7 +425,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = it.kb0; kb < it.kb1; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
-                    uint8_t* sb = sa + A_SLOTS * A_TILE_BYTES;
+                    uint8_t* sb = sa + SAV * A_TILE_BYTES;
                     if (p.mode == 1) {
                         mbar_arrive(&full[stage]);
                         if (++stage == STAGES) {
@@ -464,7 +469,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full[stage], phase, p.err);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint32_t a_lo = desc_lo_sw64(sa), b_lo = desc_lo_sw64(sa + A_SLOTS * A_TILE_BYTES);
+                    const uint32_t a_lo = desc_lo_sw64(sa), b_lo = desc_lo_sw64(sa + SAV * A_TILE_BYTES);
                     if (p.mode == 2) {
                     } else if (it.is_h) {
                         if (kb == it.kb0) issue_h<BN, true>(tmem_base, a_lo, b_lo);
