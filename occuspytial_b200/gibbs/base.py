@@ -255,9 +255,13 @@ class GibbsBase:
         if local <= 0:
             return []
         arrays = {k: v[lo:hi] for k, v in arrays.items()}
+        import time as _time
+        t_begin = _time.perf_counter()
         engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8)
         try:
             engine.set_start(self._start_to_engine(arrays))
+            t_setup = _time.perf_counter() - t_begin
+            t_sweep = t_flush = 0.0
             draws = size - burnin
             dims = {'alpha': engine.r, 'beta': engine.p, 'tau': 1}
             per_draw = 8 * local * sum(dims.values())
@@ -271,9 +275,10 @@ class GibbsBase:
             done, filled, flushed = 0, 0, 0
 
             def flush():
-                nonlocal filled, flushed
+                nonlocal filled, flushed, t_flush
                 if not filled:
                     return
+                t0 = _time.perf_counter()
                 for k, d in dims.items():
                     part = record[k][:, :filled].cpu().numpy()
                     engine.d2h_bytes += part.nbytes
@@ -283,10 +288,12 @@ class GibbsBase:
                         host[k][:, flushed:flushed + filled] = part.reshape(host[k][:, flushed:flushed + filled].shape)
                 flushed += filled
                 filled = 0
+                t_flush += _time.perf_counter() - t0
 
             fails = 0
             while done < size:
                 step = min(block, size - done)
+                t0 = _time.perf_counter()
                 if done < burnin:
                     step = min(step, burnin - done)
                     fails = engine.sweep(step)
@@ -294,8 +301,9 @@ class GibbsBase:
                     step = min(step, capacity - filled)
                     fails = engine.sweep(step, record, rec_start=filled)
                     filled += step
-                    if filled == capacity:
-                        flush()
+                t_sweep += _time.perf_counter() - t0
+                if done >= burnin and filled == capacity:
+                    flush()
                 done += step
                 bar.update(step)
             flush()
@@ -304,7 +312,8 @@ class GibbsBase:
                 raise RuntimeError(f'Cholesky factorization/solver failed! ({fails} of {local} chains)')
             self._pull_state(engine)
             self._last_stats = dict(launches=engine.launches, h2d_bytes=engine.h2d_bytes,
-                                    d2h_bytes=engine.d2h_bytes, chains=local, chain_offset=lo)
+                                    d2h_bytes=engine.d2h_bytes, chains=local, chain_offset=lo,
+                                    seconds=dict(setup=t_setup, sweeps=t_sweep, flush=t_flush))
         finally:
             engine.close()
         out = ChainViews(host)
