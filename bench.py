@@ -60,8 +60,8 @@ def config_dict(args, wl):
                         f'V={wl["V"]} visit rows, RSR rank q={wl["q"]}, {args.chains} chains per GPU',
             'chains_per_gpu': args.chains, 'n_sites': wl['n'], 'rsr_rank_q': wl['q'], 'visit_rows': wl['V'],
             'parallelism': f'chains sharded over {args.gpus} GPU(s), no per-iteration collective',
-            'l2_policy': 'per-step working set (psi 8 B + omega/z byte planes 7 B per site and chain ~ 0.6 GB, plus the '
-                         '0.25 GB of Z slices) exceeds the 126 MB L2'}
+            'l2_policy': 'per-step working set (omega/z byte planes 5 B per site and chain ~ 0.2 GB, the 0.15 GB of Z slices, '
+                         'the 77 MB of Gram rows) exceeds the 126 MB L2'}
 
 
 # --------------------------------------------------------------------------------------------------
