@@ -81,14 +81,17 @@ def main():
         for chains in (int(c) for c in args.c5_chains.split(',')):
             run(f'c5_{chains}', s, chains, max(5, args.steps // 3), 5,
                 f'LogitRSR n=50000 (200x250), q=64, {chains} chains; data + constructor {ctor:.1f} s')
-    if 'q' in only:
+    if only & {'q', 'q256', 'q512'}:
         # second series of SURVEY 8(d): larger RSR ranks (tiled large-q solve, tcgen05 Gram over ~34k / ~51k columns)
         from occuspytial_b200.gibbs import _setup
         Q, W, X, y, *_ = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random_state=0)
         for q in (256, 512):
+            if not only & {'q', f'q{q}'}:
+                continue
             K = _setup.rsr_basis(Q, X, q=q)
             s = LogitRSRGibbs(Q, W, X, y, random_state=10, K=K)
             run(f'q{q}', s, 1024, max(5, args.steps // 3), 5, f'LogitRSR n=10000, q={q}, 1024 chains')
+    if only & {'q', 'r05'}:
         Q, W, X, y, *_ = make_data(n=2500, min_v=2, max_v=8, lattice=(50, 50), random_state=0)
         s = LogitRSRGibbs(Q, W, X, y, random_state=10)          # default threshold r = 0.5
         run('r05_2500', s, 1024, max(5, args.steps // 3), 5,

@@ -29,6 +29,8 @@ static inline void philox_round_keys(uint64_t seed, PhiloxKeys& rk) {
     }
 }
 
+constexpr int PHILOX_FAST_ROUNDS = 7;
+
 struct Philox {
     uint32_t ctr[4];
     uint32_t key[2];
@@ -69,10 +71,14 @@ struct Philox {
         have = 4;
     }
 
+    // ROUNDS = 7 (Philox4x32-7, the smallest round count of the family that passes BigCrush, Salmon et al. 2011 table 2)
+    // is used by the production PG / truncated-normal draws of the site pass, whose cost is dominated by this function;
+    // everything else keeps the conventional 10.
+    template <int ROUNDS = 10>
     __device__ __forceinline__ void refill_rk(const PhiloxKeys& rk) {
         uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
 #pragma unroll
-        for (int i = 0; i < 10; i++) {
+        for (int i = 0; i < ROUNDS; i++) {
             const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
             const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
             c0 = hi1 ^ c1 ^ rk.k[2 * i];
@@ -126,7 +132,7 @@ struct RT<float> {
     // four uniforms from exactly one Philox block, round keys from the kernel parameters; (0, 1): the word is
     // truncated to 24 significant bits (round toward zero) and centred by 2^-33
     static __device__ __forceinline__ void unif4_rk(Philox& g, const PhiloxKeys& rk, float& a, float& b, float& c, float& d) {
-        g.refill_rk(rk);
+        g.refill_rk<PHILOX_FAST_ROUNDS>(rk);
         g.have = 0;
         a = fmaf(__uint2float_rz(g.buf[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
         b = fmaf(__uint2float_rz(g.buf[1]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);

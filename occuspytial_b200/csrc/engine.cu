@@ -50,7 +50,7 @@ static bool fuse_psi(const occu_engine* e) {
     }
     // beyond ~128 columns of [X K] the in-pass DMMA product (no operand reuse across the 8-site sub-tiles) costs more
     // than the tiled GEMM plus the psi round trip (measured at q = 1256: 2.7 vs 1.3 ms per 1024 chains)
-    return allowed && e->v.model == OCCU_LOGIT_RSR && !e->pg_fp64 && e->v.pq <= 128;
+    return allowed && (e->v.model == OCCU_LOGIT_RSR || e->v.model == OCCU_PROBIT_RSR) && !e->pg_fp64 && e->v.pq <= 128;
 }
 
 template <typename PGT, bool SLICES, bool FUSE_PSI>
@@ -76,15 +76,17 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
     if (v.model == OCCU_PROBIT_RSR) {
         dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
         switch (v.r) {
-#define CASE(R)                                                                             \
-    case R:                                                                                 \
-        if (e->pg_fp64) site_pass_probit_kernel<R, true><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);  \
-        else site_pass_probit_kernel<R, false><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);            \
+#define CASE(R)                                                                                             \
+    case R:                                                                                                 \
+        if (e->pg_fp64) site_pass_probit_kernel<R, true, false><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);       \
+        else if (fuse_psi(e)) site_pass_probit_kernel<R, false, true><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);  \
+        else site_pass_probit_kernel<R, false, false><<<grid, CHAIN_TILE, 0, st>>>(v, dbg);                  \
         break;
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
         }
         e->launches++;
+        e->omega_in_slices = v.zprob == nullptr;   // omega_b = d + eps, materialised on request (debug engines store it)
     } else if (v.int8) {
         // the site pass writes the digits of (omega, z) for the tcgen05 Gram itself
         if (!e->pg_fp64 && e->low_planes_dirty) {   // an injected 48-bit omega was sliced earlier: clear its low planes
@@ -479,7 +481,21 @@ __global__ void omega_from_slices_kernel(View v) {
     v.omega[idx] = (double)q * (1.0 / 35184372088832.0);
 }
 
+// probit production engines do not store omega_b: the site pass leaves d = omega_b - eps and eps
+__global__ void omega_from_d_eps_kernel(View v) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (size_t)v.n * v.Cp) v.omega[idx] = v.kd[idx] + v.eps[idx];
+}
+
 static int materialise_omega(occu_engine* e, cudaStream_t st) {
+    if (e->v.model == OCCU_PROBIT_RSR && e->omega_in_slices) {
+        const size_t total = (size_t)e->v.n * e->v.Cp;
+        omega_from_d_eps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->v);
+        e->launches++;
+        e->omega_in_slices = false;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (!(e->v.int8 && e->slices_valid && e->omega_in_slices)) return 0;
     const size_t total = (size_t)e->v.n * e->v.Cp;
     omega_from_slices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->v);

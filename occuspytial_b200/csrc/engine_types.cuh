@@ -116,7 +116,7 @@ struct occu_engine {
     bool slices_valid;      // Aq holds the digits of the current (omega, z)
     int omega_planes;       // omega byte planes that can be non-zero: SA_F32 after a production (FP32) site pass, else SA
     bool low_planes_dirty;  // planes SA_F32 .. SA - 1 hold digits of an older 48-bit omega
-    bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines)
+    bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines; probit: omega_b = d + eps)
     int profiling;
     double kernel_ms[KC_COUNT];
     long long kernel_calls[KC_COUNT];
@@ -190,11 +190,12 @@ static int fill_dims(const occu_problem_t* P, View& v) {
         v.tc_Mrows = g.Mrows;
     }
     if (P->model == OCCU_PROBIT_RSR) {
-        // only the K-split product U'd runs: split it until the grid covers the GPU (2 CTAs x 148 SMs)
-        const int tiles = (v.Cp / dgemm::BM) * (v.ldh / dgemm::BN);
-        int ks = (296 + tiles - 1) / tiles;
+        // only the K-split product U'd runs.  The split depends on n alone (never on the number of chains): it fixes the
+        // FP64 summation order, and a chain's draws must not change with the shard it runs in.  >= 32 K tiles per split,
+        // at most 16 splits: n = 10^4 gives 16, so that even one 128-chain tile spreads over 32 CTAs
         const int kt = v.n_pad / dgemm::BK;
-        v.ksplit = ks < 1 ? 1 : (ks > kt ? kt : (ks > 64 ? 64 : ks));
+        const int ks = kt / 32;
+        v.ksplit = ks < 1 ? 1 : (ks > 16 ? 16 : ks);
     }
     v.n_tiles = (P->n + SITE_TILE - 1) / SITE_TILE;
     v.NV = P->r * (P->r + 1) / 2 + P->r;

@@ -249,11 +249,12 @@ __device__ __forceinline__ double truncnorm_draw(double loc, bool positive, Phil
 // Production-precision variant: the same draw with the transcendental work in FP32 (one 32-bit uniform for the
 // inverse-CDF branch).  Like the PG draws these are latent random variates, not deterministic quantities; the
 // KS tests against scipy.stats.truncnorm arbitrate (tests/test_gpu_primitives.py).
-__device__ __forceinline__ double truncnorm_draw_f32(double loc, bool positive, Philox& g) {
+// `word`: the 32 random bits of the inverse-CDF branch; `g`: generator for the (rare) far-tail rejection branch
+__device__ __forceinline__ double truncnorm_word_f32(double loc, bool positive, uint32_t word, Philox& g) {
     const float a = positive ? -(float)loc : (float)loc;
     float x;
     if (a < 5.0f) {
-        const float u = ((float)(g.next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u = fmaf(__uint2float_rz(word), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
         const float pa = normcdff(-a);
         x = -normcdfinvf(pa * u);   // u and 1 - u are exchangeable
         x = fmaxf(x, a);
@@ -269,11 +270,20 @@ __device__ __forceinline__ double truncnorm_draw_f32(double loc, bool positive, 
     return positive ? loc + xd : loc - xd;
 }
 
+__device__ __forceinline__ double truncnorm_draw_f32(double loc, bool positive, Philox& g) {
+    const uint32_t word = g.next_u32();
+    return truncnorm_word_f32(loc, positive, word, g);
+}
+
 // N(0,1) in FP32 (Box-Muller, 32-bit uniform for the radius: tail to 6.6 sigma)
-__device__ __forceinline__ double normal_f32(Philox& g) {
-    const float u1 = ((float)g.next_u32() + 0.5f) * (1.0f / 4294967296.0f);
-    const float u2 = g.unif_f();
+__device__ __forceinline__ double normal_words_f32(uint32_t w1, uint32_t w2) {
+    const float u1 = fmaf(__uint2float_rz(w1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u2 = (float)(w2 >> 8) * (1.0f / 16777216.0f);
     return (double)(sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
+}
+__device__ __forceinline__ double normal_f32(Philox& g) {
+    const uint32_t w1 = g.next_u32(), w2 = g.next_u32();
+    return normal_words_f32(w1, w2);
 }
 
 // Gamma(shape, 1): Marsaglia & Tsang (2000); shape < 1 through the U^(1/shape) boost.

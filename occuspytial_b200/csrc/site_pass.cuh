@@ -6,15 +6,23 @@
 // site pass (logit): z-update, omega_a draws + alpha partial sums, omega_b draw
 //
 // CTA = 128 chains x SITE_TILE sites, thread = chain.
-//  phase 1 (lock-step over the tile's sites, coalesced): z | psi, alpha in FP64; z, kd written; psi kept
-//          in shared memory as the PG argument; z bits kept in a register.
-//  phase 2 (lanes desynchronise): every lane walks its OWN stream of PG draws -- for each site the visits
-//          of an occupied surveyed site (omega_a) and then the site itself (omega_b) -- running one
-//          rejection round per loop trip (pg1_round).  An accepted lane commits and immediately fetches
-//          its next draw, a rejected lane retries: no lane waits for another lane's rejection loop.
-//  phase 3: omega_b (staged in the lane's own shared-memory column) is written out coalesced.
-// Philox streams are keyed by (chain, visit row | site, iteration, stage), so the result does not
-// depend on how lanes interleave.
+//  phase 1 (lock-step over the tile's sites, coalesced): z | psi, alpha; z written; psi kept in shared memory as
+//          the PG argument; the z bits and the set of sites whose visits need omega_a draws kept in registers.
+//          The occupancy probability is evaluated in FP32 log2 space by production engines (it only feeds a
+//          Bernoulli draw) and in FP64 by debug / validation engines, which expose it for the 1e-10 parity tests.
+//  phase 2 (lanes desynchronise): one rejection round of the PG sampler per loop trip (pg1_round).  Two kinds of work:
+//          * omega_a: every lane walks ITS OWN list of visit rows (the visits of the sites its chain occupies); the
+//            accepted draw goes into the lane's FP64 accumulators of W_e' Om_a W_e and W_e'(y_e - 1/2), so this work is
+//            tied to the lane;
+//          * omega_b: the SITE_TILE x 32 draws PG(1, psi) of a warp are a POOL: arguments and results live in shared
+//            memory, so any lane can serve any (site, chain) pair.  A lane without a visit draw takes the next pool
+//            task (warp ballot + prefix count: no atomics).  The pool evens out the lanes' different list lengths and
+//            rejection counts -- all 32 lanes stay busy until both kinds of work run out together.
+//          An accepted lane commits and fetches its next draw in the same trip, a rejected lane retries: no lane waits
+//          for another lane's rejection loop ("compaction by refill").
+//  phase 3: omega_b (shared memory) is written out coalesced.
+// Philox streams are keyed by (chain, visit row | site, iteration, stage), so the result does not depend on which
+// lane served a draw or on how lanes interleave.
 // ------------------------------------------------------------------------------------------------
 //  SLICES (tcgen05 Gram path): phase 3 writes omega as SA base-256 digits of its 48-bit fixed-point value and z as one
 //          more byte plane, site-contiguous per chain (gram_tc.cuh: Aq[s][chain][site]) -- the A operand of the Gram
@@ -26,16 +34,49 @@ constexpr int site_min_blocks(int r) { return r <= 4 ? 8 : (r <= 6 ? 5 : 3); }
 //          per warp and step, operands straight from L1/L2), instead of by a separate GEMM that writes psi [n x chains]
 //          to HBM for this kernel to read back: the DMMA work hides under the ALU-bound PG sampling of the other warps.
 constexpr int PSI_SUB = 8;   // sites per DMMA sub-tile
+// psi[ib .. ib + 8)[32 chains of this warp] = U theta:  D (8 sites x 8 chains) += A (8 x 4: UT'[site][k]) B (4 x 8:
+// theta[k][chain]); rows of UT and theta beyond pq are zero up to kq_pad.  Result in psi_d[site][chain column of the CTA];
+// a warp only touches its own 32 columns.
+__device__ __forceinline__ void psi_subtile_dmma(const View& v, int ib, int tid, int c, double (*psi_d)[CHAIN_TILE]) {
+    const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int cw = c - lane;   // first chain of this warp
+    const size_t Cp = v.Cp;
+    double acc[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) acc[nb][0] = acc[nb][1] = 0.0;
+    const double* ua = v.UT + (size_t)t4 * v.n_pad + ib + g;       // n_pad >= i0 + SITE_TILE: no bounds check
+    const double* tb = v.theta + (size_t)t4 * Cp + cw + g;
+    const int ksteps = (v.pq + 3) >> 2;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ks++) {
+        const double a = ua[(size_t)ks * 4 * v.n_pad];
+        double b[4];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) b[nb] = tb[(size_t)ks * 4 * Cp + nb * 8];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[nb][0], acc[nb][1], a, b[nb]);
+    }
+    __syncwarp();   // the previous sub-tile's readers are done
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {
+        psi_d[g][(tid & ~31) + nb * 8 + 2 * t4] = acc[nb][0];
+        psi_d[g][(tid & ~31) + nb * 8 + 2 * t4 + 1] = acc[nb][1];
+    }
+    __syncwarp();
+}
 template <int R, typename PGT, bool SLICES, bool FUSE_PSI>
 __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
+    static_assert(SITE_TILE <= 64, "per-lane site masks are 64-bit");
     extern __shared__ __align__(16) unsigned char site_smem[];
-    PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // column tid is private to thread tid
+    PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // psi in, omega_b out
     // FUSE_PSI: FP64 psi of the current sub-tile, [PSI_SUB][CHAIN_TILE]; a warp only touches its own 32 columns
     double (*psi_d)[CHAIN_TILE] = reinterpret_cast<double(*)[CHAIN_TILE]>(site_smem + sizeof(PGT) * SITE_TILE * CHAIN_TILE);
     const int tid = threadIdx.x;
     const uint32_t iter = v.ctl->iter;
     const bool first = v.ctl->first != 0;
+    // FP64 occupancy probabilities: validation build and debug engines (which dump them, OCCU_F_ZPROB)
+    const bool zf64 = std::is_same<PGT, double>::value || v.zprob != nullptr;
     const size_t Cp = v.Cp;
     const int tile = blockIdx.x;
     const int c = blockIdx.y * CHAIN_TILE + tid;
@@ -48,37 +89,11 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
     for (int k = 0; k < R; k++) al[k] = v.alpha[(size_t)k * Cp + c];
 
     // ---- phase 1: z | . ----
-    uint64_t zbits = 0ull;
+    uint64_t zbits = 0ull;   // z of the tile's sites
+    uint64_t pend = 0ull;    // sites whose visits get omega_a draws: surveyed and occupied
     static_assert(SITE_TILE % PSI_SUB == 0, "whole DMMA sub-tiles");
     for (int ib = i0; ib < i1; ib += PSI_SUB) {
-    if (FUSE_PSI) {
-        // psi[ib .. ib + 8)[32 chains of this warp] = U theta:  D (8 sites x 8 chains) += A (8 x 4: UT'[site][k]) B (4 x 8:
-        // theta[k][chain]); rows of UT and theta beyond pq are zero up to kq_pad
-        const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-        const int cw = c - lane;   // first chain of this warp
-        double acc[4][2];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) acc[nb][0] = acc[nb][1] = 0.0;
-        const double* ua = v.UT + (size_t)t4 * v.n_pad + ib + g;       // n_pad >= i0 + SITE_TILE: no bounds check
-        const double* tb = v.theta + (size_t)t4 * Cp + cw + g;
-        const int ksteps = (v.pq + 3) >> 2;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ks++) {
-            const double a = ua[(size_t)ks * 4 * v.n_pad];
-            double b[4];
-#pragma unroll
-            for (int nb = 0; nb < 4; nb++) b[nb] = tb[(size_t)ks * 4 * Cp + nb * 8];
-#pragma unroll
-            for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[nb][0], acc[nb][1], a, b[nb]);
-        }
-        __syncwarp();   // the previous sub-tile's readers are done
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-            psi_d[g][(tid & ~31) + nb * 8 + 2 * t4] = acc[nb][0];
-            psi_d[g][(tid & ~31) + nb * 8 + 2 * t4 + 1] = acc[nb][1];
-        }
-        __syncwarp();
-    }
+    if (FUSE_PSI) psi_subtile_dmma(v, ib, tid, c, psi_d);
     for (int i = ib; i < min(ib + PSI_SUB, i1); i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
@@ -94,88 +109,128 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
                 // logit.py:241-245 / 249:  pr = expit(psi) prod / (1 - expit(psi) + expit(psi) prod) with
                 // prod = prod_j expit(-w_ij alpha)  ==  1 / (1 + exp(-psi) prod_j (1 + exp(w_ij alpha))): one exp per
                 // visit and one division per site; not-surveyed sites have the empty product
-                double grow = exp(-psi);
-                if (cls == OCCU_SITE_NOT_OBS) {
-                    const int v1 = v.visit_ptr[i + 1];
-                    for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
-                        double lin = 0.0;
-#pragma unroll
-                        for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
-                        grow *= 1.0 + exp(lin);
-                    }
-                }
-                const double pr = 1.0 / (1.0 + grow);
-                if (v.zprob) v.zprob[off] = pr;
                 Philox g;
                 g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
                 g.refill_rk(v.rk);
-                const uint64_t bits = ((uint64_t)g.buf[0] << 21) ^ (uint64_t)(g.buf[1] >> 11);  // == g.unif_d()
-                zc = ((double)bits + 0.5) * (1.0 / 9007199254740992.0) < pr ? 1 : 0;  // logit.py:246 / 250
+                if (zf64) {
+                    double grow = exp(-psi);
+                    if (cls == OCCU_SITE_NOT_OBS) {
+                        const int v1 = v.visit_ptr[i + 1];
+                        for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            grow *= 1.0 + exp(lin);
+                        }
+                    }
+                    const double pr = 1.0 / (1.0 + grow);
+                    if (v.zprob) v.zprob[off] = pr;
+                    const uint64_t bits = ((uint64_t)g.buf[0] << 21) ^ (uint64_t)(g.buf[1] >> 11);  // == g.unif_d()
+                    zc = ((double)bits + 0.5) * (1.0 / 9007199254740992.0) < pr ? 1 : 0;  // logit.py:246 / 250
+                } else {
+                    // same probability in FP32 log2 space (MUFU ex2 / lg2): lg = log2(exp(-psi) prod (1 + exp(w alpha)));
+                    // an overflowing factor gives lg = +inf and probability 0, its limit
+                    float lg = -1.4426950408889634f * (float)psi;
+                    if (cls == OCCU_SITE_NOT_OBS) {
+                        const int v1 = v.visit_ptr[i + 1];
+                        for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            lg += f_lg2(1.0f + f_ex2(1.4426950408889634f * (float)lin));
+                        }
+                    }
+                    // z = 1 with probability 1 / (1 + grow):  U < 1 / (1 + grow)  <=>  U (1 + grow) < 1; a small U
+                    // keeps its full relative precision (the integer is converted with a floating exponent)
+                    const float u = fmaf(__uint2float_rz(g.buf[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+                    zc = u * (1.0f + f_ex2(lg)) < 1.0f ? 1 : 0;
+                }
             }
             v.z[off] = (uint8_t)zc;
             if (!SLICES) v.kd[off] = (double)zc - 0.5;  // logit.py:252
         }
         zbits |= (uint64_t)zc << (i - i0);
+        if (cls != OCCU_SITE_NOT_SURVEYED && zc) pend |= 1ull << (i - i0);
         arg_s[i - i0][tid] = (PGT)psi;
     }
     }  // sub-tiles
+    __syncwarp();   // phase 2 reads the warp's 32 columns of arg_s across lanes
 
-    // ---- phase 2: per-lane stream of PG draws ----
+    // ---- phase 2: PG draws ----
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
-    int i = i0 - 1, vv = 0, vend = 0, cur = 0;
-    bool site_done = true, active = true, have = false, is_visit = false;
+    const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int wbase = tid - lane;              // first column of this warp within the tile
+    const uint32_t gcw = gc - (uint32_t)lane;  // global chain id of the warp's first lane
+    const int pool_total = (i1 - i0) * 32;     // omega_b draws of this warp, task = site-in-tile * 32 + chain-in-warp
+    int pool_next = 0;                         // warp-uniform: next task not handed out yet
+    int vv = 0, vend = 0, cur = 0;
+    bool have = false, is_visit = false;
     typename PGSel<PGT>::Task task;
     Philox g;
     double wv[R];  // design row of the visit being drawn (kept from the fetch to the commit)
 #pragma unroll
     for (int k = 0; k < R; k++) wv[k] = 0.0;
-    while (__any_sync(0xffffffffu, active || have)) {
-        if (!have && active) {
-            // next draw of this lane's stream, loop-free: the visits of an occupied surveyed site
-            // (omega_a ~ PG(1, w_ij alpha), logit.py:187-193), then the site itself (omega_b ~ PG(1, psi),
-            // logit.py:201-204), then the next site
-            if (vv >= vend && site_done) {
-                if (++i >= i1) {
-                    active = false;
-                } else {
-                    site_done = false;
-                    if (v.site_class[i] != OCCU_SITE_NOT_SURVEYED && ((zbits >> (i - i0)) & 1ull)) {
-                        vv = v.visit_ptr[i];
-                        vend = v.visit_ptr[i + 1];
-                    }
-                }
+    for (;;) {
+        // -- fetch: the lane's next visit draw (omega_a ~ PG(1, w_ij alpha), logit.py:187-193), else a pool task
+        //    (omega_b ~ PG(1, psi), logit.py:201-204) --
+        bool fetched = false, want_pool = false;
+        PGT carg = (PGT)0;
+        uint32_t pchain = gc, pelem = 0u, pstage = ST_OMEGA_A;
+        if (!have) {
+            if (vv >= vend && pend) {   // next occupied surveyed site of this lane's chain
+                const int s = __ffsll((long long)pend) - 1;
+                pend &= pend - 1ull;
+                vv = v.visit_ptr[i0 + s];
+                vend = v.visit_ptr[i0 + s + 1];
             }
-            if (active) {
-                PGT carg;
-                is_visit = vv < vend;
-                if (is_visit) {
-                    cur = vv++;
-                    double lin = 0.0;
+            if (vv < vend) {
+                cur = vv++;
+                double lin = 0.0;
 #pragma unroll
-                    for (int k = 0; k < R; k++) {
-                        wv[k] = v.W[(size_t)cur * R + k];
-                        lin += wv[k] * al[k];
-                    }
-                    carg = (PGT)lin;
-                } else {
-                    site_done = true;
-                    cur = i;
-                    carg = arg_s[i - i0][tid];
+                for (int k = 0; k < R; k++) {
+                    wv[k] = v.W[(size_t)cur * R + k];
+                    lin += wv[k] * al[k];
                 }
-                g.init(v.seed, gc, (uint32_t)cur, iter, is_visit ? ST_OMEGA_A : ST_OMEGA_B);
-                PGSel<PGT>::setup(carg, task);  // one shared copy of the setup code for both kinds of draw
-                have = true;
+                carg = (PGT)lin;
+                pelem = (uint32_t)cur;
+                is_visit = true;
+                fetched = true;
+            } else {
+                want_pool = true;
             }
         }
+        const unsigned wants = __ballot_sync(0xffffffffu, want_pool);
+        if (wants) {
+            const int mine = pool_next + __popc(wants & lt_mask);
+            pool_next += __popc(wants);
+            if (want_pool && mine < pool_total) {
+                cur = mine;
+                const int s = mine >> 5, ch = mine & 31;
+                carg = arg_s[s][wbase + ch];
+                pchain = gcw + (uint32_t)ch;
+                pelem = (uint32_t)(i0 + s);
+                pstage = ST_OMEGA_B;
+                is_visit = false;
+                fetched = true;
+            }
+        }
+        if (fetched) {
+            g.init(v.seed, pchain, pelem, iter, pstage);
+            PGSel<PGT>::setup(carg, task);  // one copy of the setup code for both kinds of draw
+            have = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        // -- one rejection round --
         if (have) {
             PGT ub, ux, u3, us, x;
             RT<PGT>::unif4_rk(g, v.rk, ub, ux, u3, us);
             if (PGSel<PGT>::round(task, ub, ux, u3, us, x)) {
                 have = false;
-                const double om = 0.25 * (double)x;
                 if (is_visit) {
+                    const double om = 0.25 * (double)x;
                     const double yk = (double)v.y[cur] - 0.5;
                     int idx = 0;
 #pragma unroll
@@ -187,11 +242,12 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
 #pragma unroll
                     for (int a = 0; a < R; a++) acc[NA + a] = fma(wv[a], yk, acc[NA + a]);  // logit.py:223
                 } else {
-                    arg_s[cur - i0][tid] = (PGT)om;
+                    arg_s[cur >> 5][wbase + (cur & 31)] = (PGT)0.25 * x;
                 }
             }
         }
     }
+    __syncwarp();   // phase 3 reads the lane's own column, written by whichever lane served the task
 
     // ---- phase 3: write-out ----
     if (!SLICES)
@@ -300,11 +356,20 @@ struct SiteDebug {
 // ------------------------------------------------------------------------------------------------
 // site pass (probit): z | ., omega_a (truncated normal) + alpha partial sums, omega_b, eps, d = omega_b - eps
 // No rejection loops (inverse-CDF draws), so the lanes stay in lock-step over the sites of the tile.
+//
+// Production precision (F64 = false, nothing injected): the latent draws and the occupancy probability run in FP32
+// (normcdff / normcdfinvf; KS tests arbitrate, tests/test_gpu_primitives.py), ONE Philox4x32-7 block serves a site
+// (words: z | omega_b | two for the eps normal) and one block serves four visits of a site; psi = [X K] theta is formed
+// here on the FP64 tensor pipe (FUSE_PSI, as in the logit pass) and only eps, d and z cross HBM (25 B per site and
+// chain; omega_b = d + eps is materialised on request).  Debug / validation engines keep FP64 everywhere, one
+// Philox4x32-10 stream per draw, and also store omega_b and the occupancy probability.
 // ------------------------------------------------------------------------------------------------
-template <int R, bool F64>
-__global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
+template <int R, bool F64, bool FUSE_PSI>
+__global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
-    const int c = blockIdx.y * CHAIN_TILE + threadIdx.x;
+    __shared__ __align__(16) double psi_d[FUSE_PSI ? PSI_SUB : 1][CHAIN_TILE];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.y * CHAIN_TILE + tid;
     const int tile = blockIdx.x;
     const int i0 = tile * SITE_TILE;
     const int i1 = min(i0 + SITE_TILE, v.n);
@@ -313,6 +378,8 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View
     const uint32_t gc = (uint32_t)(v.chain_offset + c);
     const size_t Cp = v.Cp;
     const int cr = c % v.C;
+    // FP64 draws / probabilities: validation build, debug engines (they dump the probabilities) and injected randomness
+    const bool slow = F64 || v.zprob != nullptr || dbg.u_site != nullptr || dbg.u_visit != nullptr || dbg.nrm_eps != nullptr;
 
     double al[R];
 #pragma unroll
@@ -321,79 +388,149 @@ __global__ void __launch_bounds__(CHAIN_TILE) site_pass_probit_kernel(const View
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
-    for (int i = i0; i < i1; i++) {
+    for (int ib = i0; ib < i1; ib += PSI_SUB) {
+    if (FUSE_PSI) psi_subtile_dmma(v, ib, tid, c, psi_d);
+    for (int i = ib; i < min(ib + PSI_SUB, i1); i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
-        const double lp = v.psi[off];   // x_i beta + K_i eta
+        const double lp = FUSE_PSI ? psi_d[i - ib][tid] : v.psi[off];   // x_i beta + K_i eta
+        if (FUSE_PSI && v.zprob) v.psi[off] = lp;                       // debug engines keep psi readable
         const double ep = v.eps[off];
+        const double loc = lp + ep;
         const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
         int zc;
-        if (keep_z) {
-            zc = v.z[off];
-        } else {
-            if (cls == OCCU_SITE_OBS) {
-                zc = 1;
+        double omb, nz;
+        if (slow) {
+            // ---- FP64 path: one Philox stream per draw ----
+            if (keep_z) {
+                zc = v.z[off];
             } else {
-                double pr = ndtr_d(lp + ep);  // probit.py:251 / 258
-                if (cls == OCCU_SITE_NOT_OBS) {
-                    double prod = 1.0;  // probit.py:252-253: prod_j (1 - Phi(w_ij alpha))
-                    for (int vv = v0; vv < v1; vv++) {
-                        double lin = 0.0;
-#pragma unroll
-                        for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
-                        prod *= 1.0 - ndtr_d(lin);
-                    }
-                    const double num = pr * prod;
-                    pr = num / ((1.0 - pr) + num);  // probit.py:254-255
-                }
-                if (v.zprob) v.zprob[off] = pr;
-                Philox g;
-                g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
-                zc = g.unif_d() < pr ? 1 : 0;
-            }
-            v.z[off] = (uint8_t)zc;
-        }
-        if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
-            // omega_a ~ TN(w_ij alpha, 1) on (0, inf) if y_ij = 1 else (-inf, 0)   (probit.py:180-194)
-            for (int vv = v0; vv < v1; vv++) {
-                double w[R];
-                double lin = 0.0;
-#pragma unroll
-                for (int k = 0; k < R; k++) {
-                    w[k] = v.W[(size_t)vv * R + k];
-                    lin += w[k] * al[k];
-                }
-                const bool positive = v.y[vv] == 1;
-                double oma;
-                if (dbg.u_visit) {
-                    oma = truncnorm_icdf(lin, positive, dbg.u_visit[(size_t)cr * v.V + vv]);
+                if (cls == OCCU_SITE_OBS) {
+                    zc = 1;
                 } else {
+                    double pr = ndtr_d(loc);  // probit.py:251 / 258
+                    if (cls == OCCU_SITE_NOT_OBS) {
+                        double prod = 1.0;  // probit.py:252-253: prod_j (1 - Phi(w_ij alpha))
+                        for (int vv = v0; vv < v1; vv++) {
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            prod *= 1.0 - ndtr_d(lin);
+                        }
+                        const double num = pr * prod;
+                        pr = num / ((1.0 - pr) + num);  // probit.py:254-255
+                    }
+                    if (v.zprob) v.zprob[off] = pr;
                     Philox g;
-                    g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
-                    oma = F64 ? truncnorm_draw(lin, positive, g) : truncnorm_draw_f32(lin, positive, g);
+                    g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
+                    zc = g.unif_d() < pr ? 1 : 0;
                 }
-                int idx = 0;
-#pragma unroll
-                for (int a = 0; a < R; a++) {
-#pragma unroll
-                    for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
-                }
-#pragma unroll
-                for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
+                v.z[off] = (uint8_t)zc;
             }
+            if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
+                // omega_a ~ TN(w_ij alpha, 1) on (0, inf) if y_ij = 1 else (-inf, 0)   (probit.py:180-194)
+                for (int vv = v0; vv < v1; vv++) {
+                    double w[R];
+                    double lin = 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; k++) {
+                        w[k] = v.W[(size_t)vv * R + k];
+                        lin += w[k] * al[k];
+                    }
+                    const bool positive = v.y[vv] == 1;
+                    double oma;
+                    if (dbg.u_visit) {
+                        oma = truncnorm_icdf(lin, positive, dbg.u_visit[(size_t)cr * v.V + vv]);
+                    } else {
+                        Philox g;
+                        g.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
+                        oma = F64 ? truncnorm_draw(lin, positive, g) : truncnorm_draw_f32(lin, positive, g);
+                    }
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < R; a++) {
+#pragma unroll
+                        for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
+                    }
+#pragma unroll
+                    for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
+                }
+            }
+            // omega_b ~ TN(lp + eps, 1), sign by z (probit.py:196-209); eps | . (probit.py:216-221)
+            Philox g;
+            g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
+            omb = dbg.u_site ? truncnorm_icdf(loc, zc == 1, dbg.u_site[(size_t)cr * v.n + i])
+                             : (F64 ? truncnorm_draw(loc, zc == 1, g) : truncnorm_draw_f32(loc, zc == 1, g));
+            nz = dbg.nrm_eps ? dbg.nrm_eps[(size_t)cr * v.n + i] : (F64 ? g.normal_d() : normal_f32(g));
+        } else {
+            // ---- production path: FP32 latent draws, one Philox block per site and per four visits ----
+            Philox g;
+            g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
+            g.refill_rk<PHILOX_FAST_ROUNDS>(v.rk);
+            g.have = 0;
+            const uint32_t wz = g.buf[0], wb = g.buf[1], wn1 = g.buf[2], wn2 = g.buf[3];
+            if (keep_z) {
+                zc = v.z[off];
+            } else {
+                if (cls == OCCU_SITE_OBS) {
+                    zc = 1;
+                } else {
+                    // z = 1 with probability num / (den + num), num = Phi(loc) prod_j Phi(-w_ij alpha), den = Phi(-loc)
+                    float num = normcdff((float)loc);
+                    const float den = normcdff(-(float)loc);
+                    if (cls == OCCU_SITE_NOT_OBS) {
+                        for (int vv = v0; vv < v1; vv++) {
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            num *= normcdff(-(float)lin);
+                        }
+                    }
+                    const float u = fmaf(__uint2float_rz(wz), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+                    zc = u * (den + num) < num ? 1 : 0;   // probit.py:254-260
+                }
+                v.z[off] = (uint8_t)zc;
+            }
+            if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
+                for (int vg = v0; vg < v1; vg += 4) {
+                    Philox ga;
+                    ga.init(v.seed, gc, (uint32_t)vg, iter, ST_OMEGA_A);
+                    ga.refill_rk<PHILOX_FAST_ROUNDS>(v.rk);
+                    ga.have = 0;
+                    const uint32_t wd[4] = {ga.buf[0], ga.buf[1], ga.buf[2], ga.buf[3]};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int vv = vg + j;
+                        if (vv < v1) {
+                            double w[R];
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < R; k++) {
+                                w[k] = v.W[(size_t)vv * R + k];
+                                lin += w[k] * al[k];
+                            }
+                            const double oma = truncnorm_word_f32(lin, v.y[vv] == 1, wd[j], ga);
+                            int idx = 0;
+#pragma unroll
+                            for (int a = 0; a < R; a++) {
+#pragma unroll
+                                for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
+                            }
+#pragma unroll
+                            for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
+                        }
+                    }
+                }
+            }
+            omb = truncnorm_word_f32(loc, zc == 1, wb, g);   // probit.py:196-209
+            nz = normal_words_f32(wn1, wn2);
         }
-        // omega_b ~ TN(lp + eps, 1), sign by z (probit.py:196-209); eps | . (probit.py:216-221)
-        Philox g;
-        g.init(v.seed, gc, (uint32_t)i, iter, ST_OMEGA_B);
-        const double loc = lp + ep;
-        const double omb = dbg.u_site ? truncnorm_icdf(loc, zc == 1, dbg.u_site[(size_t)cr * v.n + i])
-                                      : (F64 ? truncnorm_draw(loc, zc == 1, g) : truncnorm_draw_f32(loc, zc == 1, g));
-        const double nz = dbg.nrm_eps ? dbg.nrm_eps[(size_t)cr * v.n + i] : (F64 ? g.normal_d() : normal_f32(g));
-        const double ep_new = 0.5 * (omb - lp) + nz * 0.70710678118654752440;
-        v.omega[off] = omb;
+        const double ep_new = 0.5 * (omb - lp) + nz * 0.70710678118654752440;   // probit.py:216-221
+        if (v.zprob) v.omega[off] = omb;   // debug engines keep omega_b readable as drawn; else omega_b = d + eps on request
         v.eps[off] = ep_new;
         v.kd[off] = omb - ep_new;  // d: right-hand-side vector of both the eta and the beta systems
     }
+    }  // sub-tiles
 #pragma unroll
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
 }

@@ -87,7 +87,9 @@ class DeviceEngine:
             nbytes = self.lib.occu_workspace_bytes(C.byref(P))
             if nbytes == 0:
                 _lib.check(-1, 'occu_workspace_bytes')
-            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            # allocated (and later freed) in the context of the engine's stream: it is the only stream that touches it
+            with torch.cuda.stream(self.stream):
+                self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
             base = (self.workspace.data_ptr() + 255) // 256 * 256
             handle = C.c_void_p()
             _lib.check(self.lib.occu_create(C.byref(P), base, nbytes, self.stream.cuda_stream, C.byref(handle)),
@@ -113,14 +115,15 @@ class DeviceEngine:
             _lib.check(self.lib.occu_set_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_set_field')
             self.stream.synchronize()
 
-    def get_field(self, field):
+    def get_field(self, field, chain=None):
+        """Chain-major host copy of a state field, (chains, dim); ``chain=k`` copies only that chain, (1, dim)."""
         torch = self.torch
         dtype = torch.uint8 if field == _lib.F_Z else torch.float64
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             t = torch.empty((self.chains,) + self._field_shape(field), dtype=dtype, device=self.device)
             _lib.check(self.lib.occu_get_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_get_field')
             self.stream.synchronize()
-            out = t.cpu().numpy()
+            out = (t if chain is None else t[chain:chain + 1]).cpu().numpy()
         self.d2h_bytes += out.nbytes
         return out
 
@@ -137,7 +140,9 @@ class DeviceEngine:
     # ---- sampling ------------------------------------------------------------------------------
     def alloc_record(self, capacity):
         torch = self.torch
-        with torch.cuda.device(self.device):
+        # the zero fill runs on the engine's stream, the same one the sweeps record on (a fill on the default stream
+        # could land after the first recorded draws: torch streams do not synchronise with each other)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             return {
                 'alpha': torch.zeros((self.chains, capacity, self.r), dtype=torch.float64, device=self.device),
                 'beta': torch.zeros((self.chains, capacity, self.p), dtype=torch.float64, device=self.device),

@@ -22,6 +22,16 @@ from .parallel import sample_parallel, shard_bounds, dist_info
 _RECORD_BYTES = 2 << 30
 
 
+def _check_visits_match(w_ptr, y_ptr):
+    """W and y must describe the same visits: same surveyed sites, same number of visits per site.  The kernels
+    index y with W's visit offsets, so a mismatch would silently misalign every later site (the reference fails
+    with a shape error in ``W.T @ y``, logit.py:223)."""
+    if w_ptr.shape != y_ptr.shape or not np.array_equal(w_ptr, y_ptr):
+        bad = np.flatnonzero(np.diff(w_ptr) != np.diff(y_ptr))
+        where = f' (first mismatch at site {int(bad[0])})' if bad.size else ''
+        raise ValueError('W and y must have the same surveyed sites and the same number of visits per site' + where)
+
+
 class _GibbsState(State):
     """Sampler state; ``posteriors`` returns the stored parameters (base.py:15-27)."""
 
@@ -174,7 +184,8 @@ class GibbsBase:
         f = self.fixed
         n = f.n
         W_rows, visit_ptr = self.W.to_csr(n)
-        y_rows, _ = self.y.to_csr(n, dtype=np.uint8)
+        y_rows, y_ptr = self.y.to_csr(n, dtype=np.uint8)
+        _check_visits_match(visit_ptr, y_ptr)
         return dict(X=self.X, W_rows=W_rows.reshape(W_rows.shape[0], -1), y_rows=y_rows, visit_ptr=visit_ptr,
                     site_class=f.site_class, tau_rate=f.tau_rate, tau_shape=f.tau_shape,
                     a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
@@ -223,14 +234,13 @@ class GibbsBase:
 
     def _pull_state(self, engine):
         from .. import _lib
-        self.state.alpha = engine.get_field(_lib.F_ALPHA)[0]
-        self.state.beta = engine.get_field(_lib.F_BETA)[0]
-        self.state.tau = float(engine.get_field(_lib.F_TAU)[0])
-        self.state.eta = self._eta_from_engine(engine.get_field(_lib.F_ETA)[0])
+        self.state.alpha = engine.get_field(_lib.F_ALPHA, chain=0)[0]
+        self.state.beta = engine.get_field(_lib.F_BETA, chain=0)[0]
+        self.state.tau = float(engine.get_field(_lib.F_TAU, chain=0)[0])
+        self.state.eta = self._eta_from_engine(engine.get_field(_lib.F_ETA, chain=0)[0])
         self.state.spatial = self._spatial_from_eta(self.state.eta)
-        if engine.chains <= 64:
-            self.state.z = self._sites_from_engine(engine.get_field(_lib.F_Z)[0].astype(np.float64))
-            self.state.k = self.state.z - 0.5
+        self.state.z = self._sites_from_engine(engine.get_field(_lib.F_Z, chain=0)[0].astype(np.float64))
+        self.state.k = self.state.z - 0.5
 
     def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None,
                       pg_fp64=False, gram_int8=None):
@@ -252,7 +262,11 @@ class GibbsBase:
         arrays = self._start_arrays(chains, start)
         lo, hi = shard_bounds(chains, world, rank)
         local = hi - lo
-        if local <= 0:
+        self._last_arrays = None
+        self._last_stats = None
+        if local <= 0:   # more ranks than chains: this rank holds an empty shard
+            dims = {'alpha': self.W[self.W.surveyed[0]].shape[1], 'beta': self.X.shape[1], 'tau': 1}
+            self._last_arrays = {k: np.empty((0, size - burnin) + ((d,) if d > 1 else ())) for k, d in dims.items()}
             return []
         arrays = {k: v[lo:hi] for k, v in arrays.items()}
         import time as _time
@@ -355,7 +369,7 @@ class GibbsBase:
         samples = sample_parallel(self, size=size, burnin=burnin, chains=chains, start=start,
                                   progressbar=progressbar, **engine_kwargs)
         stacked = getattr(self, '_last_arrays', None)
-        if samples and stacked is not None and stacked['tau'].shape[0] == len(samples):
+        if stacked is not None and stacked['tau'].shape[0] == len(samples):
             return PosteriorParameter.from_arrays(stacked)  # already (chains, draws[, dim]): skip np.stack
         return PosteriorParameter(*samples)
 

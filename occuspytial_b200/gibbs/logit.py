@@ -6,7 +6,7 @@ alpha, z -- logit.py:254-266) runs in the CUDA engine, see occuspytial_b200/csrc
 import numpy as np
 
 from . import _setup
-from .base import GibbsBase
+from .base import GibbsBase, _check_visits_match
 
 
 class LogitICARGibbs(GibbsBase):
@@ -59,7 +59,8 @@ class LogitICARGibbs(GibbsBase):
         n = f.n
         inv = self._inv
         W_rows, visit_ptr = Data({int(inv[s]): self.W[s] for s in self.W.surveyed}).to_csr(n)
-        y_rows, _ = Data({int(inv[s]): self.y[s] for s in self.y.surveyed}).to_csr(n, dtype=np.uint8)
+        y_rows, y_ptr = Data({int(inv[s]): self.y[s] for s in self.y.surveyed}).to_csr(n, dtype=np.uint8)
+        _check_visits_match(visit_ptr, y_ptr)
         return dict(X=np.ascontiguousarray(self.X[perm]), W_rows=W_rows.reshape(W_rows.shape[0], -1), y_rows=y_rows,
                     visit_ptr=visit_ptr, site_class=np.ascontiguousarray(f.site_class[perm]),
                     Qband=_setup.lower_band(f.Q, perm, bw), icar_bw=bw,

@@ -75,7 +75,8 @@ def test_full_size_sharding_and_determinism(big):
     ((100, 120), 12, 5, 3, 3),     # n = 12000: two K chunks + fixed-order reduction
     ((33, 34), 33, 200, 3, 3),     # ragged everything: n = 1122, 2 chain tiles (one partial)
     ((37, 57), 100, 129, 3, 3),    # n = 2109, 5253 Gram columns, 129 chains
-    ((32, 40), 17, 70, 5, 2)])     # other covariate counts (p = 5, r = 2): other template instances, pq = 22
+    ((32, 40), 17, 70, 5, 2),      # other covariate counts (p = 5, r = 2): other template instances, pq = 22
+    ((200, 250), 12, 3, 3, 3)])    # BASELINE config 5's site count: n = 50 000, five K chunks
 def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains, p, r):
     """The Omega-weighted Gram of the tcgen05 kind::i8 path (csrc/gram_tc.cuh) at sizes the small parity cases do
     not reach: every Gaussian system built from it agrees with a NumPy FP64 evaluation to 1e-10
@@ -156,3 +157,64 @@ def test_device_moran_basis_is_an_eigenbasis():
     v /= np.linalg.norm(v)
     top_outside = float(v @ op.matvec(v).ravel())
     assert top_outside <= lam[0] + 1e-6
+
+
+def test_omega_planes_at_large_arguments():
+    """The 32-bit omega planes of the production precision at PG arguments up to |psi| = 60 (omega ~ 1 / (2 |psi|), below
+    2^-6: the regime where the fixed-point value is ROUNDED to 2^-29 rather than exact), and the saturation of the
+    48-bit slicing of an injected omega >= 8.  Reference: logit.py:195-204 (omega_b), 325-337 (its Gram)."""
+    from occuspytial_b200 import LogitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.gibbs import _setup
+    from oracle import sweep as S
+    shape, q, chains = (32, 40), 9, 256
+    n = shape[0] * shape[1]
+    Q, W, X, y, *_ = make_data(n=n, min_v=2, max_v=5, lattice=shape, random_state=3)
+    K = _setup.rsr_basis(Q, X, q=q)
+    s = LogitRSRGibbs(Q, W, X, y, random_state=4, K=K)
+    f = s.fixed
+    rng = np.random.default_rng(2)
+    eng = s._make_engine(chains, seed=3, debug=True, gram_int8=True)
+    # column 0 of X is the intercept: beta_0 sets the level of psi; chains span |psi| ~ 0 .. 60, both signs
+    level = np.linspace(-60, 60, chains)
+    beta = np.zeros((chains, 3))
+    beta[:, 0] = level
+    st = dict(alpha=rng.normal(size=(chains, 3)), beta=beta, tau=np.ones(chains), eta=0.1 * rng.normal(size=(chains, q)))
+    eng.set_start(st)
+    eng.debug_site_half()
+    psi = eng.get_field(_lib.F_PSI)
+    omega = eng.get_field(_lib.F_OMEGA)          # the value the byte planes hold (debug engines write it from the digits)
+    assert np.abs(psi).max() > 55
+    assert np.all(omega > 0) and np.all(omega < 8)
+    scaled = omega * 2.0 ** 29
+    np.testing.assert_array_equal(scaled, np.rint(scaled))      # a 32-bit fixed-point number of omega / 8
+    assert (omega < 2.0 ** -6).mean() > 0.3                     # the rounded regime is exercised
+    # law of large numbers per |psi| band: PG(1, psi) mean and variance survive the rounding
+    resid = (omega - S.pg1_mean(psi)) / np.sqrt(S.pg1_var(psi))
+    for lo, hi in ((0, 5), (5, 20), (20, 40), (40, 61)):
+        m = (np.abs(psi) >= lo) & (np.abs(psi) < hi)
+        assert m.sum() > 10000
+        assert abs(resid[m].mean()) < 4 / np.sqrt(m.sum()) + 1e-3, (lo, hi, resid[m].mean())
+        assert abs(resid[m].var() - 1) < 0.05, (lo, hi, resid[m].var())
+    # the Gram built from those planes is the FP64 Gram of exactly these omega
+    z = eng.get_field(_lib.F_Z).astype(float)
+    normals = rng.normal(size=(chains, q + 6))
+    out = eng.debug_gaussian_half(normals=normals, tau=st['tau'])
+    assert out['fails'] == 0
+    for c in (0, 1, chains // 2, chains - 1):
+        Lam, b = S.eta_rsr_system(f.K, X, omega[c], z[c] - 0.5, st['beta'][c], st['tau'][c], f.Q)
+        np.testing.assert_allclose(out['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
+        np.testing.assert_allclose(out['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+    # injected omega beyond the fixed-point range saturates at 8 - 2^-45 instead of wrapping
+    om2 = rng.uniform(0.01, 0.4, size=omega.shape)
+    om2[:, ::7] = 8.0 + rng.uniform(0, 100, size=om2[:, ::7].shape)
+    eng.set_start(st)
+    eng.set_field(_lib.F_OMEGA, om2)
+    out2 = eng.debug_gaussian_half(normals=normals, tau=st['tau'])
+    z2 = eng.get_field(_lib.F_Z).astype(float)
+    clipped = np.minimum(om2, 8.0 - 2.0 ** -45)
+    for c in (0, chains - 1):
+        Lam, b = S.eta_rsr_system(f.K, X, clipped[c], z2[c] - 0.5, st['beta'][c], st['tau'][c], f.Q)
+        # b is formed from omega as well: only Lambda is a pure function of the sliced value
+        np.testing.assert_allclose(out2['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
+    eng.close()

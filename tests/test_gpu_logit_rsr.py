@@ -194,14 +194,17 @@ def test_chain_draws_do_not_depend_on_sharding():
     full.close(), shard.close()
 
 
-def test_posterior_vs_reference_chains():
-    """Posterior means of alpha, beta, tau within 3 MCSE of the reference's chains (golden/posterior.npz)."""
+@pytest.mark.parametrize('gram_int8', [None, True])
+def test_posterior_vs_reference_chains(gram_int8):
+    """Posterior means of alpha, beta, tau within 3 MCSE of the reference's chains (golden/posterior.npz), through the
+    engine's default path for this size (FP64 DMMA Gram) and with the production path of the headline benchmark forced
+    (tcgen05 kind::i8 Gram from the 32-bit omega planes, psi fused into the site pass)."""
     from occuspytial_b200 import LogitRSRGibbs
     from occuspytial_b200.diagnostics import summaries_from_draws, ess
     g = golden('posterior.npz')
     hp = {k[3:]: (float(v) if v.ndim == 0 else v) for k, v in g.items() if k.startswith('hp_')}
     s = _sampler_from_golden(g, LogitRSRGibbs, K=g['K'], hparams=hp, random_state=21)
-    post = s.sample(1500, burnin=500, chains=256, progressbar=False)
+    post = s.sample(1500, burnin=500, chains=256, progressbar=False, gram_int8=gram_int8)
 
     def mean_mcse(x):
         x = x.reshape(x.shape[0], x.shape[1], -1)

@@ -128,3 +128,65 @@ def test_probit_sampler_api_and_posterior_vs_oracle():
     for name in ('alpha', 'beta', 'tau'):
         for (mr, sr), (mm, sm) in zip(mean_mcse(ref[name]), mean_mcse(post[name])):
             assert abs(mr - mm) < 3.0 * np.hypot(sr, sm), (name, mr, mm, sr, sm)
+
+
+def test_probit_full_size_invariants():
+    """BASELINE config 3 at full size (n = 10 000, q = 64, 4096 chains on one device) through size-independent
+    properties of one sweep: sign(omega_b) = 2 z - 1 (probit.py:196-209), the probability integral transform of the
+    truncated normals is uniform, eps | . ~ N((omega_b - psi) / 2, 1/2) (probit.py:216-221), detections imply occupancy."""
+    from scipy.special import ndtr
+    from occuspytial_b200 import ProbitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from occuspytial_b200.gibbs import _setup
+    Q, W, X, y, alpha, *_ = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random_state=0)
+    K = _setup.rsr_basis(Q, X, q=64)
+    s = ProbitRSRGibbs(Q, W, X, y, random_state=10, K=K)
+    C = 4096
+    eng = s._make_engine(C, seed=99)
+    eng.set_start(s._start_arrays(C, None))
+    rec = eng.alloc_record(12)
+    assert eng.sweep(12, rec, 0) == 0
+    draws = {k: v.cpu().numpy() for k, v in rec.items()}
+    assert all(np.all(np.isfinite(v)) for v in draws.values()) and np.all(draws['tau'] > 0)
+    psi0, eps0 = eng.get_field(_lib.F_PSI), eng.get_field(_lib.F_EPS)
+    beta, eta = eng.get_field(_lib.F_BETA), eng.get_field(_lib.F_ETA)
+    np.testing.assert_allclose(psi0, beta @ s.X.T + eta @ s.fixed.K.T, rtol=1e-11, atol=1e-11)
+    eng.sweep(1)                                   # its site pass sees (psi0, eps0)
+    z = eng.get_field(_lib.F_Z)
+    omega, eps1 = eng.get_field(_lib.F_OMEGA), eng.get_field(_lib.F_EPS)
+    cls = s.fixed.site_class
+    assert set(np.unique(z)) <= {0, 1} and np.all(z[:, cls == 2] == 1)
+    assert np.all((omega > 0) == (z == 1))
+    loc = psi0 + eps0
+    ok = np.abs(loc) < 5                            # away from the far tail the PIT is numerically clean in FP64
+    pos = (z == 1) & ok
+    neg = (z == 0) & ok
+    pit = np.concatenate([((ndtr(omega - loc) - ndtr(-loc)) / ndtr(loc))[pos], (ndtr(omega - loc) / ndtr(-loc))[neg]])
+    assert pit.size > 1e7
+    assert abs(pit.mean() - 0.5) < 5e-4 and abs(pit.var() - 1 / 12) < 5e-4
+    hist = np.histogram(pit, bins=20, range=(0, 1))[0] / pit.size
+    assert np.abs(hist - 0.05).max() < 1e-3
+    e = (eps1 - 0.5 * (omega - psi0)) * np.sqrt(2.0)
+    assert abs(e.mean()) < 1e-3 and abs(e.var() - 1) < 2e-3
+    assert np.linalg.norm(np.median(draws['alpha'][:, -1], axis=0) - alpha) < 1.0
+    eng.close()
+
+
+def test_probit_chain_draws_do_not_depend_on_sharding():
+    """Chains 130..199 of a 200-chain job are bit-identical to a 70-chain engine at offset 130 (the K split of the
+    U'd product, hence its FP64 summation order, must not depend on the shard size)."""
+    from occuspytial_b200 import ProbitRSRGibbs
+    from occuspytial_b200.utils import make_data
+    Q, W, X, y, *_ = make_data(n=1200, min_v=1, max_v=5, lattice=(30, 40), random_state=6)
+    s = ProbitRSRGibbs(Q, W, X, y, random_state=3, q=20)
+    start = s._start_arrays(200, None)
+    out = []
+    for chains, off in ((200, 0), (70, 130)):
+        eng = s._make_engine(chains, seed=77, chain_offset=off)
+        eng.set_start({k: v[off:off + chains] for k, v in start.items()})
+        rec = eng.alloc_record(5)
+        assert eng.sweep(5, rec, 0) == 0
+        out.append({k: v.cpu().numpy() for k, v in rec.items()})
+        eng.close()
+    for k in ('alpha', 'beta', 'tau'):
+        np.testing.assert_array_equal(out[0][k][130:], out[1][k])
