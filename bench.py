@@ -35,7 +35,9 @@ def parse():
     ap.add_argument('--lattice', default='100x100')
     ap.add_argument('--q', type=int, default=64)
     ap.add_argument('--chains', type=int, default=4096, help='chains per GPU')
-    ap.add_argument('--cpu-iters', type=int, default=300, help='iterations per CPU-baseline chain')
+    ap.add_argument('--cpu-iters', type=int, default=150, help='iterations per CPU-baseline chain')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help="weak: --chains per GPU; strong: --chains in total, sharded over the GPUs (BASELINE config 3's wording)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--pg-fp64', action='store_true')
@@ -52,14 +54,15 @@ def workload(args):
     Q, W, X, y, *_ = make_data(n=n, min_v=2, max_v=8, lattice=(rows, cols), random_state=0)
     K = _setup.rsr_basis(Q, X, q=args.q)
     V = sum(w.shape[0] for w in W.values())
-    return dict(Q=Q, W=W, X=X, y=y, K=K, n=n, V=V, q=args.q, p=X.shape[1], r=3)
+    return dict(Q=Q, W=W, X=X, y=y, K=K, n=n, V=V, q=args.q, p=X.shape[1], r=next(iter(W.values())).shape[1])
 
 
 def config_dict(args, wl):
     return {'workload': f'LogitRSRGibbs make_data-style n={wl["n"]} ({args.lattice} queen lattice), p=r=3, '
-                        f'V={wl["V"]} visit rows, RSR rank q={wl["q"]}, {args.chains} chains per GPU',
-            'chains_per_gpu': args.chains, 'n_sites': wl['n'], 'rsr_rank_q': wl['q'], 'visit_rows': wl['V'],
-            'parallelism': f'chains sharded over {args.gpus} GPU(s), no per-iteration collective',
+                        f'V={wl["V"]} visit rows, RSR rank q={wl["q"]}, {args.chains} chains ' + ('per GPU' if args.scaling == 'weak' else 'in total'),
+            'chains_per_gpu': args.chains if args.scaling == 'weak' else -(-args.chains // args.gpus), 'n_sites': wl['n'], 'rsr_rank_q': wl['q'], 'visit_rows': wl['V'],
+            'parallelism': f'chains sharded over {args.gpus} GPU(s), no per-iteration collective; one all-gather of per-chain '
+                           'summary blocks (R-hat / ESS) at the end of sample()',
             'l2_policy': 'per-step working set (omega/z byte planes 5 B per site and chain ~ 0.2 GB, the 0.15 GB of Z slices, '
                          'the 77 MB of Gram rows) exceeds the 126 MB L2'}
 
@@ -67,30 +70,44 @@ def config_dict(args, wl):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's sweep, one process per chain over all host cores
 # --------------------------------------------------------------------------------------------------
-def _cpu_worker(payload):
-    # one BLAS thread per chain process, as the reference's loky workers are meant to run;
-    # the environment variables are too late once NumPy is loaded, so the pools are limited at run time
+_CPU_SAMPLER = None
+ITERS_PER_STEP = 10   # reference arm: one "step" = 10 Gibbs iterations of one chain per host core
+
+
+def _cpu_init(small):
+    """Pool initialiser: build the chain's sampler and warm it up OUTSIDE the timed region."""
+    global _CPU_SAMPLER
     from threadpoolctl import threadpool_limits
     from oracle import sweep as S
-    wl, seed, warm, iters = payload
+    threadpool_limits(limits=1)   # one BLAS thread per chain process, as the reference's loky workers run (BASELINE.md 4)
+    _CPU_SAMPLER = S.OracleSampler('logit_rsr', small['Q'], small['W'], small['X'], small['y'],
+                                   seed=[7, os.getpid()], K=small['K'])
+    _CPU_SAMPLER.init_state()
+    for _ in range(3):
+        _CPU_SAMPLER.step()
+
+
+def _cpu_worker(iters):
+    from threadpoolctl import threadpool_limits
     with threadpool_limits(limits=1):
-        s = S.OracleSampler('logit_rsr', wl['Q'], wl['W'], wl['X'], wl['y'], seed=seed, K=wl['K'])
-        s.init_state()
-        for _ in range(warm):
-            s.step()
         t0 = time.perf_counter()
         for _ in range(iters):
-            s.step()
+            _CPU_SAMPLER.step()
         return time.perf_counter() - t0
 
 
 def cpu_chain_iters_per_sec(wl, cores, warm, iters):
-    """Reference arm / cpu_baseline: `cores` chains in parallel processes (parallel.py:38-41 analogue)."""
+    """Reference arm / cpu_baseline: `cores` chains in parallel processes (parallel.py:38-41 analogue).  The pool is
+    started, every sampler built and `warm` iterations run before the clock starts; the timed region is `iters`
+    iterations of every chain, wall clock around the whole map (the slowest chain counts)."""
     import multiprocessing as mp
     small = {k: wl[k] for k in ('Q', 'W', 'X', 'y', 'K')}
-    with mp.get_context('fork').Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(small, [7, c], warm, iters) for c in range(cores)])
-    return cores * iters / max(times), max(times)
+    with mp.get_context('fork').Pool(cores, initializer=_cpu_init, initargs=(small,)) as pool:
+        pool.map(_cpu_worker, [max(1, warm)] * cores, chunksize=1)
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [iters] * cores, chunksize=1)
+        elapsed = time.perf_counter() - t0
+    return cores * iters / elapsed, elapsed
 
 
 def run_reference(args):
@@ -99,20 +116,23 @@ def run_reference(args):
         return
     wl = workload(args)
     cores = os.cpu_count()
-    # a "step" of this arm = one Gibbs iteration of `cores` concurrent chains (bounded sample of the workload)
-    # the CPU arm needs ~60 ms per chain-iteration: bound the sample so that the default run ends in minutes
-    steps, warm = min(args.steps, 100), min(args.warmup, 10)
-    value, elapsed = cpu_chain_iters_per_sec(wl, cores, warm, steps)
+    # a "step" of this arm = ITERS_PER_STEP Gibbs iterations of `cores` concurrent chains: a bounded sample of the
+    # workload (one chain-iteration costs ~15-60 ms on a host core) sized so that K = 20 steps already give a stable number
+    steps, warm = min(args.steps, 60), min(args.warmup, 5)
+    value, elapsed = cpu_chain_iters_per_sec(wl, cores, warm * ITERS_PER_STEP, steps * ITERS_PER_STEP)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * elapsed / steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': config_dict(args, wl),
         'cpu_baseline': {'value': value, 'unit': 'chain-iterations/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{cores} chains x {steps} iterations of the same n={wl["n"]}, q={wl["q"]} '
-                                   'workload, one process per chain (oracle/sweep.py + oracle/pg_devroye.c: NumPy/'
+                         'sample': f'{cores} chains x {steps * ITERS_PER_STEP} iterations ({steps} steps of {ITERS_PER_STEP}) '
+                                   f'of the same n={wl["n"]}, q={wl["q"]} workload, one process per chain, pool and '
+                                   'samplers warmed before the clock (oracle/sweep.py + oracle/pg_devroye.c: NumPy/'
                                    'LAPACK restatement of the reference sweep; the Python reference itself cannot '
-                                   'travel to the GPU box and needs the absent polyagamma package)'},
+                                   'travel to the GPU box and needs the absent polyagamma package; measured in the build '
+                                   'container, the port runs 1.37x the unmodified reference per core: '
+                                   'profiles/r02_reference_vs_port_cpu.json)'},
         'e2e': {'value': value, 'unit': 'chain-iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -190,6 +210,28 @@ def _emit(text):
         os.write(_JSON_FD, (text + '\n').encode())
 
 
+def int8_peak_tops(torch):
+    """Dense INT8 tensor-core rate of this GPU, measured in the run: torch._int_mm (cuBLASLt IMMA) 8192^3, best of 5."""
+    n = 8192
+    try:
+        a = torch.randint(-8, 8, (n, n), dtype=torch.int8, device='cuda')
+        b = torch.randint(-8, 8, (n, n), dtype=torch.int8, device='cuda')
+        torch._int_mm(a, b)
+        best = float('inf')
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:   # the library call is only a yardstick; fall back to the bf16-derived proxy
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -205,26 +247,27 @@ def run_b200(args):
         _JSON_FD = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    from occuspytial_b200 import LogitRSRGibbs, _lib
-    from occuspytial_b200.gibbs.parallel import allgather_summaries
+    from occuspytial_b200 import LogitRSRGibbs
+    from occuspytial_b200.gibbs.parallel import shard_bounds
 
     wl = workload(args)
     sampler = LogitRSRGibbs(wl['Q'], wl['W'], wl['X'], wl['y'], random_state=10, K=wl['K'])
-    chains_total = args.chains * world
-    lo = rank * args.chains
+    chains_total = args.chains * world if args.scaling == 'weak' else args.chains
+    lo, hi = shard_bounds(chains_total, world, rank)
+    local = hi - lo
+    dev = f'cuda:{local_rank}'
 
     # ---- device-resident timing: inputs in HBM, K iterations, CUDA events on the engine's stream ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # before the warm-up, so that short timed regions still collect samples
     seed = 12345
-    start = sampler._start_arrays(chains_total, None)
-    start = {k: v[lo:lo + args.chains] for k, v in start.items()}
-    eng = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
+    start = sampler._start_arrays_range(seed, lo, hi, None)
+    eng = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
     eng.set_start(start)
     rec = eng.alloc_record(args.steps)
     fails = eng.sweep(args.warmup)
     launches0 = eng.launches
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -244,27 +287,34 @@ def run_b200(args):
     clock_info = clocks.stop() if rank == 0 else None
     value = chains_total * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- per-kernel timing for the roofline (separate short profiled run, CUDA events per kernel class) ----
+    # ---- per-kernel timing for the rooflines (separate short profiled run, CUDA events per kernel class) ----
     eng.set_profiling(True)
     eng.sweep(min(args.steps, 10))
     kms = eng.kernel_ms()
     eng.set_profiling(False)
     gram_path = 'int8' if eng.gram_int8 else 'dmma'
-    # the only cross-GPU exchange of the method: all-gather of per-chain summary blocks for R-hat / ESS
-    lib = _lib.load()
-    max_lag = min(args.steps - 1, 20)
-    summ = torch.empty((args.chains, 1, 6 + max_lag + 1), dtype=torch.float64, device='cuda')
-    _lib.check(lib.occu_chain_summaries(rec['tau'].data_ptr(), args.chains, args.steps, 1, max_lag, summ.data_ptr(),
-                                        eng.stream.cuda_stream), 'occu_chain_summaries')
-    torch.cuda.synchronize()
-    gathered = allgather_summaries(summ, chains_total)
-    assert gathered.shape[0] == chains_total
     eng.close()
     del eng, rec
-    # the hand-written FP64 DMMA Gram kernel, measured beside the default path (rank 0 only, short run)
-    dmma_info = None
+    # the same sweep with FP64 latent draws (validation build), and the hand-written FP64 DMMA Gram: measured beside the
+    # production path (rank 0 only, short runs)
+    fp64_info, dmma_info = None, None
+    if rank == 0 and not args.pg_fp64:
+        e2 = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=True, gram_int8=GRAM[args.gram])
+        e2.set_start(start)
+        e2.sweep(3)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(e2.stream):
+            a0.record(e2.stream)
+            e2.sweep(6)
+            a1.record(e2.stream)
+        torch.cuda.synchronize()
+        fp64_info = {'value': local * 6 / (a0.elapsed_time(a1) * 1e-3), 'unit': 'chain-iterations/s (this GPU)',
+                     'ms_per_step': a0.elapsed_time(a1) / 6, 'steps': 6,
+                     'note': 'pg_fp64=True: PG draws and occupancy probabilities in FP64 (validation build), 48-bit omega planes'}
+        e2.close()
+        del e2
     if gram_path == 'int8' and rank == 0:
-        e2 = sampler._make_engine(args.chains, seed, chain_offset=lo, pg_fp64=args.pg_fp64, gram_int8=False)
+        e2 = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=args.pg_fp64, gram_int8=False)
         e2.set_start(start)
         e2.sweep(5)
         e2.set_profiling(True)
@@ -276,121 +326,146 @@ def run_b200(args):
         dmma_info = {'kernel': "dgemm::gemm_tn_kernel (hand-written FP64 DMMA Gram, gram='dmma' path)", 'ms_per_launch': g_ms,
                      'step_ms_with_this_path': sum(v[0] / max(v[1], 1) for v in k2.values())}
 
-    # ---- end to end through the public API: host data in, host draws out (allocator-warm process: the workspace of
-    # the engine above went back to torch's caching allocator and is reused, as in any second call of a session) ----
+    # ---- end to end through the public API: host data in, host draws out.  ONE timed call of sampler.sample() after one
+    # short untimed call of the same API (first-call costs: lazy kernel loading, allocator); the timed call includes its own
+    # problem upload, start values, every iteration, the device summary blocks and the D2H of the draws ----
     e2e = None
     if not args.no_e2e:
-        # untimed warm-up call of the same public API (first-call costs: lazy kernel loading, allocator, pinned staging);
-        # the timed call below still includes its own problem upload, start values, every iteration and the D2H of the draws
-        sampler.sample(max(8, args.warmup // 5), burnin=2, chains=chains_total, progressbar=False,
-                       pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
+        kw = dict(chains=chains_total, progressbar=False, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
+        if world == 1:
+            kw['device'] = dev      # one GPU, as --gpus says (a plain call would fan out over every visible GPU)
+        sampler.sample(max(8, args.warmup // 5), burnin=2, **kw)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        prof = None
-        if os.environ.get('OCCU_PROFILE_E2E'):   # debugging aid: where does the host time of the timed call go
-            import cProfile
-            prof = cProfile.Profile()
-            prof.enable()
-        dt, st = float('inf'), None
-        for _ in range(2):   # two timed calls, the faster one is reported (host-side set-up jitters by up to 0.1 s on these boxes)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, chains=chains_total, progressbar=False,
-                                  pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
-            torch.cuda.synchronize()
-            one = time.perf_counter() - t0
-            if world > 1:   # a call is as slow as its slowest rank
-                t = torch.tensor([one], dtype=torch.float64, device='cuda')
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                one = float(t.item())
-            if one < dt:
-                dt, st = one, sampler._last_stats
-        if prof is not None:
-            import pstats
-            prof.disable()
-            pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(22)
+        t0 = time.perf_counter()
+        post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = sampler._last_stats
+        if world > 1:   # a call is as slow as its slowest rank
+            t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
         iters = args.steps + args.warmup
-        assert post['tau'].shape == (args.chains, args.steps)
+        assert post['tau'].shape == (local, args.steps)
+        summ = sampler._last_summaries
+        assert summ is not None and summ['tau'].shape[0] == chains_total   # all-gathered over the ranks (NCCL)
+        h2d = torch.tensor([st['h2d_bytes'], st['d2h_bytes']], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(h2d)
         e2e = {'value': chains_total * iters / dt, 'unit': 'chain-iterations/s',
-               'h2d_bytes_per_step': st['h2d_bytes'] * world / iters, 'd2h_bytes_per_step': st['d2h_bytes'] * world / iters,
+               'h2d_bytes_per_step': float(h2d[0]) / iters, 'd2h_bytes_per_step': float(h2d[1]) / iters,
                'seconds': dict(st.get('seconds', {}), total=dt),
-               'note': f'sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) wall time incl. problem '
-                       'upload, start values, all iterations and the copy of the recorded draws to host (after one short '
-                       'untimed warm-up call; faster of two timed calls)'}
+               'r_hat_tau_from_device_summaries': float(post.summary.loc['tau', 'r_hat']),
+               'note': f'one timed sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) call, wall clock incl. '
+                       'problem upload, start values, all iterations, per-chain summary blocks (all-gathered over the ranks) '
+                       'and the copy of the recorded draws to host; one short untimed call of the same API before it'}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant step: the Omega-weighted Gram ----
+    # ---- rooflines, per kernel; `roofline` is the kernel with the largest share of the step ----
     pq = wl['p'] + wl['q']
-    n_pad = -(-wl['n'] // 128) * 128
     M = pq * (pq + 1) // 2
-    M_pad = -(-M // 64) * 64
-    gram_ms, gram_calls = kms['gram_gemm']
-    gram_ms /= gram_calls
-    gram_flops_alg = 2.0 * wl['n'] * (M + pq) * args.chains      # algorithmic FP64 flops
+    ms = {k: v[0] / max(v[1], 1) for k, v in kms.items()}
+    total_ms = sum(ms.values())
+    gram_ms = ms['gram_gemm']
+    gram_flops_alg = 2.0 * wl['n'] * (M + pq) * local           # algorithmic FP64 flops
     peak64 = fp64_peak_tflops(torch)
-    peaks = {}
+    peaks, traffic, ncu_facts = {}, {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except OSError:
         pass
+    try:   # DRAM bytes per launch and issue statistics from the committed `ncu --set full` captures (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        ncu_facts = traffic.get('_site_pass_ncu', {})
+    except (OSError, ValueError):
+        pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    total_ms = sum(v[0] / max(v[1], 1) for v in kms.values())
+    hbm_src = 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'
+    scale_traffic = local / 4096.0 * wl['n'] / 10000.0   # the captures were taken on the default workload
+
+    # site pass: z, omega_a, omega_b.  Algorithmic bytes per site and chain: z out (1) + omega/z byte planes out
+    # (5 in production precision, 7 with FP64 draws; FP64 Gram path: omega + kd, 16) + psi in (8, unless formed in the pass)
+    # + the alpha partial sums (NV doubles per 32-site tile)
+    r_ = wl['r']
+    nv = r_ * (r_ + 1) // 2 + r_
+    fused_psi = not args.pg_fp64 and os.environ.get('OCCU_FUSE_PSI', '1') != '0' and pq <= 128
+    site_b = 1 + ((7 if args.pg_fp64 else 5) if gram_path == 'int8' else 16) + (0 if fused_psi else 8) + 8.0 * nv / 32
+    site_bytes = site_b * wl['n'] * local
+    site_ms = ms['site_pass']
+    t_site = traffic.get('site_pass_logit_kernel')
+    roof_site = {'bound': 'hbm', 'kernel': 'site_pass_logit_kernel: z Bernoulli update, PG(1, .) draws for omega_a / omega_b with '
+                 'pooled refill, alpha partial sums, psi = [X K] theta on the FP64 tensor pipe, byte planes of (omega, z) out '
+                 '(csrc/site_pass.cuh)',
+                 'achieved': site_bytes / (site_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                 'frac': site_bytes / (site_ms * 1e-3) / 1e9 / hbm_peak,
+                 'traffic': None if t_site is None else t_site * scale_traffic, 'peak_source': hbm_src,
+                 'alg_bytes_per_site_chain': site_b, 'ms_per_launch': site_ms, 'share_of_step': site_ms / total_ms,
+                 'limiter': 'instruction issue, not HBM: ~2.4 PG draws per site and chain at >= 100 instructions each '
+                            '(Philox block, proposal, alternating-series test) against 8 bytes of traffic',
+                 'ncu': ncu_facts}
+    # Gram
     if gram_path == 'int8':
         # gram_tc_kernel (csrc/gram_tc.cuh): slice pairs (omega planes x 6 Z planes, levels s + t <= 7) over 128-chain x
-        # 64-column tiles, plus the 6 slices of the U'z tiles
-        # production precision: omega is a 32-bit fixed-point number (4 byte planes) -> 18 slice pairs; FP64 draws: 21
+        # 64-column tiles, plus the 6 slices of the U'z tiles; production precision: omega is a 32-bit fixed-point number
+        # (4 byte planes) -> 18 slice pairs; FP64 draws: 21.  Useful INT8 operations (no tile / K padding counted)
         PAIRS, SB = (21 if args.pg_fp64 else 18), 6
-        # useful INT8 operations of the slicing algorithm (no tile / K padding counted): PAIRS products of the
-        # [chains x n] omega planes with the [n x M] Z planes, SB products of the z plane with the [n x pq] U planes
-        int8_ops = 2.0 * args.chains * wl['n'] * (M * PAIRS + pq * SB)
-        int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
-        traffic = None
-        try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('gram_tc_kernel')
-        except (OSError, ValueError):
-            pass
-        roofline = {'bound': 'tensor', 'kernel': 'gtc::gram_tc_kernel<64>: hand-written tcgen05.mma kind::i8 (TMA-staged '
-                    'operands, 6 level accumulators in TMEM, FP64 recombination in the epilogue); exact integer evaluation '
-                    'of the FP64 contraction [Omega\' Z | z\' U] (csrc/gram_tc.cuh)',
-                    'achieved': int8_ops / (gram_ms * 1e-3) / 1e12, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
-                    'frac': int8_ops / (gram_ms * 1e-3) / 1e12 / int8_peak, 'traffic': traffic,
-                    'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (no INT8 figure is recorded; nominal dense INT8 is 4500)',
-                    'fp64_equivalent_tflops': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'fp64_dgemm_peak_tflops': peak64,
-                    'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
+        int8_ops = 2.0 * local * wl['n'] * (M * PAIRS + pq * SB)
+        int8_meas = int8_peak_tops(torch)
+        int8_peak = int8_meas if int8_meas else 2.0 * peaks.get('bf16_tflops', 1590.0)
+        t_gram = traffic.get('gram_tc_kernel')
+        roof_gram = {'bound': 'tensor', 'kernel': 'gtc::gram_tc_kernel<64>: hand-written tcgen05.mma kind::i8 (TMA-staged '
+                     'operands, 6 level accumulators in TMEM, FP64 recombination in the epilogue); exact integer evaluation '
+                     'of the FP64 contraction [Omega\' Z | z\' U] (csrc/gram_tc.cuh)',
+                     'achieved': int8_ops / (gram_ms * 1e-3) / 1e12, 'peak': int8_peak, 'unit': 'TOP/s (int8, dense)',
+                     'frac': int8_ops / (gram_ms * 1e-3) / 1e12 / int8_peak,
+                     'traffic': None if t_gram is None else t_gram * scale_traffic,
+                     'peak_source': ('torch._int_mm 8192^3 (cuBLASLt INT8 GEMM) measured in this run, best of 5' if int8_meas else
+                                     '2 x MEASURED_PEAKS.json bf16_tflops (torch._int_mm unavailable)') + '; nominal dense INT8 is 4500',
+                     'fp64_equivalent_tflops': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'fp64_dgemm_peak_tflops': peak64,
+                     'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
     else:
-        roofline = {'bound': 'tensor', 'kernel': "dgemm::gemm_tn_kernel (Gram [Omega' Z | kd' U], FP64 DMMA)",
-                    'achieved': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
-                    'frac': gram_flops_alg / (gram_ms * 1e-3) / 1e12 / peak64, 'traffic': None,
-                    'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, measured in this run (MEASURED_PEAKS.json '
-                                   'holds no FP64 figure)',
-                    'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
-    site_ms, site_calls = kms['site_pass']
-    # psi in (unless fused), z in/out, then omega + kd out (FP64 Gram path) or the 7 byte planes of (omega, z)
-    fused_psi = not args.pg_fp64 and os.environ.get('OCCU_FUSE_PSI', '1') != '0' and pq <= 128   # psi formed inside the site pass
-    site_bytes_alg = ((0 if fused_psi else 8) + 2 + ((7 if args.pg_fp64 else 5) if gram_path == 'int8' else 16)) * wl['n'] * args.chains
+        roof_gram = {'bound': 'tensor', 'kernel': "dgemm::gemm_tn_kernel (Gram [Omega' Z | kd' U], FP64 DMMA)",
+                     'achieved': gram_flops_alg / (gram_ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+                     'frac': gram_flops_alg / (gram_ms * 1e-3) / 1e12 / peak64, 'traffic': None,
+                     'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul, measured in this run (MEASURED_PEAKS.json '
+                                    'holds no FP64 figure)',
+                     'ms_per_launch': gram_ms, 'share_of_step': gram_ms / total_ms}
+    # per-chain solve: reads its packed Gram row and H, writes the state and the recorded draw
+    solve_ms = ms['solve']
+    solve_bytes = 8.0 * (M + 2 * pq + wl['p'] + r_ + 1) * local
+    t_solve = traffic.get('solve_logit_rsr_kernel')
+    roof_solve = {'bound': 'hbm', 'kernel': 'solve_logit_rsr_kernel: tau, Cholesky of K\'OmegaK + tau K\'QK in shared memory, eta, beta, '
+                  'alpha, record (csrc/solve_rsr.cuh)',
+                  'achieved': solve_bytes / (solve_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                  'frac': solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_peak,
+                  'traffic': None if t_solve is None else t_solve * local / 4096.0, 'peak_source': hbm_src,
+                  'ms_per_launch': solve_ms, 'share_of_step': solve_ms / total_ms,
+                  'limiter': 'barrier / dependent-column latency of the q x q factorisation, 6 chains per SM'}
+    roofs = {'site_pass': roof_site, 'gram_gemm': roof_gram, 'solve': roof_solve}
+    dominant = max(roofs, key=lambda k: ms[k])
     line = {
         'metric': METRIC, 'value': value, 'unit': 'chain-iterations/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(args, wl),
+        'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
+        'vs_baseline': None,
+        'dtype': 'f64' if args.pg_fp64 else 'f64 algebra (Gram, Cholesky, solves, records) / f32 latent draws (PG, z probability)',
+        'data': 'synthetic', 'config': config_dict(args, wl),
         'clocks': clock_info, 'gpu_launches': int(launches), 'failed_chains': int(fails), 'gram_path': gram_path,
-        'roofline': roofline,
-        'kernels_ms_per_step': {k: v[0] / max(v[1], 1) for k, v in kms.items()},
-        'roofline_site_pass': {'bound': 'hbm', 'achieved': site_bytes_alg / (site_ms / site_calls * 1e-3) / 1e9,
-                               'peak': hbm_peak, 'unit': 'GB/s',
-                               'frac': site_bytes_alg / (site_ms / site_calls * 1e-3) / 1e9 / hbm_peak,
-                               'note': 'the site pass is instruction-issue bound (PG sampling), not HBM bound',
-                               'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'},
+        'roofline': dict(roofs[dominant], dominant_kernel_class=dominant),
+        'kernels_ms_per_step': ms,
     }
+    for k, r in roofs.items():
+        if k != dominant:
+            line['roofline_' + {'site_pass': 'site_pass', 'gram_gemm': 'gram', 'solve': 'solve'}[k]] = r
+    if fp64_info:
+        line['value_pg_fp64'] = fp64_info
     # whole-step ceilings of SURVEY.md 8(d): F_alg / P64 (the reference's FP64 arithmetic on the FP64 pipe) and
     # B_alg / BW (every per-chain vector crossing HBM once per stage); the tcgen05 Gram leaves the first behind
-    r_ = 3
     f_alg = wl['n'] * pq * (pq + 1) + 4 * wl['n'] * pq + (wl['q'] ** 3 + wl['p'] ** 3 + r_ ** 3) / 3 \
         + 4 * (wl['q'] ** 2 + wl['p'] ** 2 + r_ ** 2) + 0.5 * wl['V'] * r_ * (r_ + 1) + 4 * wl['V'] * r_
     b_alg = 35 * wl['n'] + 16 * pq ** 2
@@ -414,7 +489,8 @@ def run_b200(args):
         v, el = cpu_chain_iters_per_sec(wl, cores, 3, args.cpu_iters)
         line['cpu_baseline'] = {'value': v, 'unit': 'chain-iterations/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{cores} chains x {args.cpu_iters} iterations of the same workload, one '
-                                          f'process per chain, {el:.1f} s (oracle/sweep.py + oracle/pg_devroye.c)'}
+                                          f'process per chain, pool and samplers warmed before the clock, {el:.1f} s '
+                                          '(oracle/sweep.py + oracle/pg_devroye.c)'}
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -36,6 +36,7 @@
 #include "solve_tiled.cuh"
 #include "primitives.cuh"
 #include "solve_icar.cuh"
+#include "solve_icar_warp.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host-side drivers
@@ -50,26 +51,33 @@ static bool fuse_psi(const occu_engine* e) {
     }
     // beyond ~128 columns of [X K] the in-pass DMMA product (no operand reuse across the 8-site sub-tiles) costs more
     // than the tiled GEMM plus the psi round trip (measured at q = 1256: 2.7 vs 1.3 ms per 1024 chains)
+    // probit debug engines keep the separate FP64 GEMM: their pass reads psi in FP64 (production forms it in FP32)
+    if (e->v.model == OCCU_PROBIT_RSR && e->debug) return false;
     return allowed && (e->v.model == OCCU_LOGIT_RSR || e->v.model == OCCU_PROBIT_RSR) && !e->pg_fp64 && e->v.pq <= 128;
 }
 
-template <typename PGT, bool SLICES, bool FUSE_PSI>
+template <typename PGT, bool SLICES, int PSI_MODE>
 static void launch_site_pass_logit(occu_engine* e, cudaStream_t st) {
     const View& v = e->v;
     dim3 grid(v.n_tiles, v.Cp / CHAIN_TILE);
-    const size_t smem = (size_t)SITE_TILE * CHAIN_TILE * sizeof(PGT) + (FUSE_PSI ? PSI_SUB * CHAIN_TILE * sizeof(double) : 0);
     switch (v.r) {
 #define CASE(R)                                                                                                      \
-    case R:                                                                                                          \
+    case R: {                                                                                                        \
+        const size_t smem = site_pass_logit_smem<PGT, R>(PSI_MODE);                                                  \
         if (smem > 48 * 1024)                                                                                        \
-            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT, SLICES, FUSE_PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        site_pass_logit_kernel<R, PGT, SLICES, FUSE_PSI><<<grid, CHAIN_TILE, smem, st>>>(v);                          \
-        break;
+            cudaFuncSetAttribute(site_pass_logit_kernel<R, PGT, SLICES, PSI_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        site_pass_logit_kernel<R, PGT, SLICES, PSI_MODE><<<grid, CHAIN_TILE, smem, st>>>(v);                          \
+        break;                                                                                                       \
+    }
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
     e->launches++;
 }
+
+// psi inside the logit site pass: FP32 only in production engines, with an FP64 staging tile when the engine dumps
+// the (FP64) occupancy probabilities
+static int psi_mode(const occu_engine* e) { return !fuse_psi(e) ? PSI_NONE : (e->v.zprob ? PSI_F64 : PSI_F32); }
 
 static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t st) {
     const View& v = e->v;
@@ -94,18 +102,21 @@ static void launch_site_pass(occu_engine* e, const SiteDebug& dbg, cudaStream_t 
             cudaMemsetAsync(v.Aq + (size_t)gtc::SA_F32 * plane, 0, (size_t)(gtc::SA - gtc::SA_F32) * plane, st);
             e->low_planes_dirty = false;
         }
-        if (e->pg_fp64) launch_site_pass_logit<double, true, false>(e, st);
-        else if (fuse_psi(e)) launch_site_pass_logit<float, true, true>(e, st);
-        else launch_site_pass_logit<float, true, false>(e, st);
+        if (e->pg_fp64) launch_site_pass_logit<double, true, PSI_NONE>(e, st);
+        else if (psi_mode(e) == PSI_F32) launch_site_pass_logit<float, true, PSI_F32>(e, st);
+        else if (psi_mode(e) == PSI_F64) launch_site_pass_logit<float, true, PSI_F64>(e, st);
+        else launch_site_pass_logit<float, true, PSI_NONE>(e, st);
         e->slices_valid = true;
         e->omega_in_slices = v.zprob == nullptr;
         e->omega_planes = e->pg_fp64 ? gtc::SA : gtc::SA_F32;
     } else if (e->pg_fp64) {
-        launch_site_pass_logit<double, false, false>(e, st);
-    } else if (fuse_psi(e)) {
-        launch_site_pass_logit<float, false, true>(e, st);
+        launch_site_pass_logit<double, false, PSI_NONE>(e, st);
+    } else if (psi_mode(e) == PSI_F32) {
+        launch_site_pass_logit<float, false, PSI_F32>(e, st);
+    } else if (psi_mode(e) == PSI_F64) {
+        launch_site_pass_logit<float, false, PSI_F64>(e, st);
     } else {
-        launch_site_pass_logit<float, false, false>(e, st);
+        launch_site_pass_logit<float, false, PSI_NONE>(e, st);
     }
 }
 
@@ -239,8 +250,27 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     e->launches += 2;
     PROF_MARK(e, KC_SOLVE, st);
     if (v.model == OCCU_LOGIT_ICAR) {
+        static int use_old = -1;   // OCCU_ICAR_KERNEL=cta selects the round-1 kernels (one CTA per chain) for A/B timing
+        if (use_old < 0) {
+            const char* sel = getenv("OCCU_ICAR_KERNEL");
+            use_old = (sel && !strcmp(sel, "cta")) ? 1 : 0;
+        }
+        if (!use_old) {
+            const size_t smem_w = icarw_smem_bytes(v.bw, v.p);
+            size_t& configured_w = e->smem_configured[0];   // per engine: the attribute is per device
+            if (smem_w > configured_w) {
+                CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+                configured_w = smem_w;
+            }
+            solve_logit_icar_warp_kernel<<<v.Cp, ICARW_THREADS, smem_w, st>>>(v, dbg, rb, rt, cap);
+            e->launches++;
+            PROF_MARK(e, KC_COUNT, st);
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
         const size_t smem_i = icar_smem_bytes(v);
-        size_t& configured_i = e->smem_configured[0];   // per engine: the attribute is per device
+        if (v.bw > 160 || smem_i > 200 * 1024) return set_err("OCCU_ICAR_KERNEL=cta: half bandwidth too large for the round-1 kernels");
+        static size_t configured_i = 0;
         if (smem_i > configured_i) {
             CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
             configured_i = smem_i;

@@ -32,6 +32,7 @@ constexpr int SITE_TILE = SITE_TILE_N;
 constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
 constexpr int SOLVE_THREADS = 128;
 constexpr int MAX_SMALL = 32;    // max p and r
+constexpr int OCCU_ICAR_MAX_BW = 200;  // 26 x 27 / 2 tiles of 512 B = 180 KB of shared memory
 constexpr int TC_BN = gtc::BN_DEFAULT;  // Z columns per tile of the tcgen05 Gram (6 level accumulators side by side in TMEM)
 
 struct Control {
@@ -162,9 +163,9 @@ static int fill_dims(const occu_problem_t* P, View& v) {
     if (P->p > MAX_SMALL || P->r > 8) return set_err("p must be <= 32 and r <= 8");
     if (!icar && P->q < 1) return set_err("RSR model needs q >= 1");
     if (icar && (P->icar_bw < 1 || P->icar_bw >= P->n)) return set_err("ICAR model needs 1 <= icar_bw < n");
-    if (icar && (P->icar_bw > 160 ||
-                 ((size_t)(P->icar_bw + 1) * (P->icar_bw + 2) + 8 * (size_t)(P->icar_bw + 1) + 4096) * 8 > 200 * 1024))
-        return set_err("ICAR half bandwidth too large for the shared-memory window (reorder the sites)");
+    // the window of the banded factorisation (8 x 8 tiles over bw + 8 rows, solve_icar_warp.cuh) lives in shared memory
+    if (icar && P->icar_bw > OCCU_ICAR_MAX_BW)
+        return set_err("ICAR half bandwidth too large for the shared-memory window (200 in this build; reorder the sites)");
     v.bw = icar ? P->icar_bw : 0;
     v.model = P->model;
     v.n = P->n; v.p = P->p; v.r = P->r; v.q = icar ? 0 : P->q; v.V = P->V;

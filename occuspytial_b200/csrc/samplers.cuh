@@ -249,15 +249,68 @@ __device__ __forceinline__ double truncnorm_draw(double loc, bool positive, Phil
 // Production-precision variant: the same draw with the transcendental work in FP32 (one 32-bit uniform for the
 // inverse-CDF branch).  Like the PG draws these are latent random variates, not deterministic quantities; the
 // KS tests against scipy.stats.truncnorm arbitrate (tests/test_gpu_primitives.py).
+// ---------------------------------------------------------------------------------------------
+// FP32 building blocks of the production probit pass (all transcendental work is single MUFU instructions; the
+// coefficients are least-squares fits made by benchmarks/fits/fit_probit_f32.py, which also prints the error bounds;
+// the KS tests against scipy.stats.truncnorm arbitrate, tests/test_gpu_primitives.py).
+//   erfc_pos_fast(z), z >= 0:  t exp(-z^2 + P(t)), t = 1 / (1 + z / 2)  (the form of Numerical Recipes' erfcc, refit to
+//                              degree 9: 3.3e-7 in exact arithmetic, 4e-6 relative as evaluated in FP32 up to z = 6)
+//   ndtri_fast(p), 0 < p < 1:  |p - 1/2| <= 0.425: (p - 1/2) A(s) / B(s), s = 0.180625 - (p - 1/2)^2; tails: rational in
+//                              r = sqrt(-ln min(p, 1 - p)) (the split of Wichura's AS241, refit: 3.1e-7 / 4.6e-7 relative
+//                              in FP32 down to p = 1e-19)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float erfc_pos_fast(float z) {
+    const float t = f_rcp(fmaf(0.5f, z, 1.0f));
+    float p = 1.879873355e-01f;
+    p = fmaf(p, t, -9.019287893e-01f);
+    p = fmaf(p, t, 1.645356232e+00f);
+    p = fmaf(p, t, -1.304344333e+00f);
+    p = fmaf(p, t, 3.878528898e-01f);
+    p = fmaf(p, t, -2.291440062e-01f);
+    p = fmaf(p, t, 1.068652698e-01f);
+    p = fmaf(p, t, 3.727594862e-01f);
+    p = fmaf(p, t, 1.000110509e+00f);
+    p = fmaf(p, t, -1.265514260e+00f);
+    return t * f_ex2(1.4426950408889634f * fmaf(-z, z, p));
+}
+
+// Phi(x) and Phi(-x) from one erfc evaluation
+__device__ __forceinline__ void phi_pair_fast(float x, float& phi, float& phi_neg) {
+    const float e = 0.5f * erfc_pos_fast(fabsf(x) * 0.70710678118654752f);   // Phi(-|x|)
+    const float big = 1.0f - e;
+    phi = x >= 0.0f ? big : e;
+    phi_neg = x >= 0.0f ? e : big;
+}
+
+__device__ __forceinline__ float ndtri_fast(float p) {
+    const float d = p - 0.5f;
+    if (fabsf(d) <= 0.425f) {
+        const float s = fmaf(-d, d, 0.180625f);
+        const float num = fmaf(fmaf(fmaf(5.505418006e+01f, s, 1.531967914e+02f), s, 4.966260758e+01f), s, 3.387132222e+00f);
+        const float den = fmaf(fmaf(fmaf(6.338554050e+01f, s, 7.627822074e+01f), s, 1.766729577e+01f), s, 1.0f);
+        return d * num * f_rcp(den);
+    }
+    const float q = d < 0.0f ? p : 1.0f - p;
+    const float L = -0.6931471805599453f * f_lg2(q);   // >= 2.59
+    const float r = L * f_rsqrt(L);
+    const float num = fmaf(fmaf(fmaf(1.710931907e+00f, r, 4.151230509e+00f), r, -1.414777384e+00f), r, -2.684062117e+00f);
+    const float den = fmaf(fmaf(fmaf(1.019275364e-04f, r, 1.206112088e+00f), r, 3.015726461e+00f), r, 1.0f);
+    const float y = num * f_rcp(den);                   // -ndtri(q) > 0
+    return d < 0.0f ? -y : y;
+}
+
 // `word`: the 32 random bits of the inverse-CDF branch; `g`: generator for the (rare) far-tail rejection branch
 __device__ __forceinline__ double truncnorm_word_f32(double loc, bool positive, uint32_t word, Philox& g) {
     const float a = positive ? -(float)loc : (float)loc;
     float x;
     if (a < 5.0f) {
         const float u = fmaf(__uint2float_rz(word), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-        const float pa = normcdff(-a);
-        x = -normcdfinvf(pa * u);   // u and 1 - u are exchangeable
-        x = fmaxf(x, a);
+        float pa_neg, pa;
+        phi_pair_fast(a, pa_neg, pa);   // pa = Phi(-a): mass of the kept side
+        x = -ndtri_fast(pa * u);        // u and 1 - u are exchangeable
+        // the approximations can land a few 1e-6 on the wrong side of the truncation point: reflect back inside, and stay
+        // strictly inside (the support is open)
+        x = a + fmaxf(fabsf(x - a), 1e-7f * (1.0f + fabsf(a)));
     } else {
         const float lam = 0.5f * (a + sqrtf(a * a + 4.0f));
         for (;;) {
@@ -277,9 +330,10 @@ __device__ __forceinline__ double truncnorm_draw_f32(double loc, bool positive, 
 
 // N(0,1) in FP32 (Box-Muller, 32-bit uniform for the radius: tail to 6.6 sigma)
 __device__ __forceinline__ double normal_words_f32(uint32_t w1, uint32_t w2) {
-    const float u1 = fmaf(__uint2float_rz(w1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float u2 = (float)(w2 >> 8) * (1.0f / 16777216.0f);
-    return (double)(sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
+    const float u1 = fmaf(__uint2float_rz(w1), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // < 1
+    const float ang = ((float)(w2 >> 8) - 8388608.0f) * (6.283185307179586f / 16777216.0f);          // [-pi, pi)
+    const float r2 = -1.3862943611198906f * f_lg2(u1);                                               // -2 ln u1 > 0
+    return (double)(r2 * f_rsqrt(r2) * f_cos(ang));
 }
 __device__ __forceinline__ double normal_f32(Philox& g) {
     const uint32_t w1 = g.next_u32(), w2 = g.next_u32();

@@ -33,56 +33,106 @@ constexpr int site_min_blocks(int r) { return r <= 4 ? 8 : (r <= 6 ? 5 : 3); }
 //  FUSE_PSI: psi = [X K] theta of the tile is computed here, on the FP64 tensor pipe (DMMA m8n8k4: 8 sites x 32 chains
 //          per warp and step, operands straight from L1/L2), instead of by a separate GEMM that writes psi [n x chains]
 //          to HBM for this kernel to read back: the DMMA work hides under the ALU-bound PG sampling of the other warps.
-constexpr int PSI_SUB = 8;   // sites per DMMA sub-tile
-// psi[ib .. ib + 8)[32 chains of this warp] = U theta:  D (8 sites x 8 chains) += A (8 x 4: UT'[site][k]) B (4 x 8:
-// theta[k][chain]); rows of UT and theta beyond pq are zero up to kq_pad.  Result in psi_d[site][chain column of the CTA];
-// a warp only touches its own 32 columns.
-__device__ __forceinline__ void psi_subtile_dmma(const View& v, int ib, int tid, int c, double (*psi_d)[CHAIN_TILE]) {
+// psi[SITE_TILE sites][32 chains of this warp] = U theta on the FP64 tensor pipe:  D (8 sites x 8 chains) += A (8 x 4:
+// UT'[site][k]) B (4 x 8: theta[k][chain]); rows of UT and theta beyond pq are zero up to kq_pad.  The loop nest keeps one
+// block of 8 chains fixed and sweeps k once for all the tile's sites, so every element of theta is read ONCE per tile (it
+// comes from L2: 0.5 MB per 128 chains) and the small UT tile (SITE_TILE x pq, shared by the CTA's warps) is what gets
+// re-read, from L1.  Result into dst[site][chain column of the CTA]; a warp only touches its own 32 columns.
+template <typename OutT>
+__device__ __forceinline__ void psi_tile_dmma(const View& v, int i0, int tid, int c, OutT (*dst)[CHAIN_TILE]) {
+    constexpr int SB = SITE_TILE / 8;
     const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int cw = c - lane;   // first chain of this warp
     const size_t Cp = v.Cp;
-    double acc[4][2];
-#pragma unroll
-    for (int nb = 0; nb < 4; nb++) acc[nb][0] = acc[nb][1] = 0.0;
-    const double* ua = v.UT + (size_t)t4 * v.n_pad + ib + g;       // n_pad >= i0 + SITE_TILE: no bounds check
-    const double* tb = v.theta + (size_t)t4 * Cp + cw + g;
     const int ksteps = (v.pq + 3) >> 2;
-#pragma unroll 4
-    for (int ks = 0; ks < ksteps; ks++) {
-        const double a = ua[(size_t)ks * 4 * v.n_pad];
-        double b[4];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) b[nb] = tb[(size_t)ks * 4 * Cp + nb * 8];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) dgemm::dmma884(acc[nb][0], acc[nb][1], a, b[nb]);
-    }
-    __syncwarp();   // the previous sub-tile's readers are done
-#pragma unroll
+    const double* ua = v.UT + (size_t)t4 * v.n_pad + i0 + g;       // n_pad >= i0 + SITE_TILE: no bounds check
+#pragma unroll 1
     for (int nb = 0; nb < 4; nb++) {
-        psi_d[g][(tid & ~31) + nb * 8 + 2 * t4] = acc[nb][0];
-        psi_d[g][(tid & ~31) + nb * 8 + 2 * t4 + 1] = acc[nb][1];
+        double acc[SB][2];
+#pragma unroll
+        for (int sb = 0; sb < SB; sb++) acc[sb][0] = acc[sb][1] = 0.0;
+        const double* tb = v.theta + (size_t)t4 * Cp + cw + nb * 8 + g;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ks++) {
+            const double b = tb[(size_t)ks * 4 * Cp];
+            double a[SB];
+#pragma unroll
+            for (int sb = 0; sb < SB; sb++) a[sb] = ua[(size_t)ks * 4 * v.n_pad + sb * 8];
+#pragma unroll
+            for (int sb = 0; sb < SB; sb++) dgemm::dmma884(acc[sb][0], acc[sb][1], a[sb], b);
+        }
+#pragma unroll
+        for (int sb = 0; sb < SB; sb++) {
+            dst[sb * 8 + g][(tid & ~31) + nb * 8 + 2 * t4] = (OutT)acc[sb][0];
+            dst[sb * 8 + g][(tid & ~31) + nb * 8 + 2 * t4 + 1] = (OutT)acc[sb][1];
+        }
     }
     __syncwarp();
 }
-template <int R, typename PGT, bool SLICES, bool FUSE_PSI>
+// PSI_MODE: 0 = psi read from v.psi (separate GEMM), 1 = formed here with an FP64 staging tile (debug / validation engines:
+// the occupancy probability is FP64), 2 = formed here and kept in FP32 only (production: two DMMA passes of 16 sites
+// write straight into the PG argument tile).
+constexpr int PSI_NONE = 0, PSI_F64 = 1, PSI_F32 = 2;
+// shared-memory copy of the tile's visit rows (design row + y - 1/2): rows that fit 7 KB
+constexpr int site_stage_rows(int r) { return 7168 / (8 * (r + 1)); }
+template <typename PGT, int R>
+constexpr size_t site_pass_logit_smem(int psi_mode) {
+    return sizeof(PGT) * SITE_TILE * CHAIN_TILE + (psi_mode == PSI_F64 ? SITE_TILE * CHAIN_TILE * sizeof(double) : 0) +
+           (size_t)site_stage_rows(R) * (R + 1) * sizeof(double) + (SITE_TILE + 4) * sizeof(int) + SITE_TILE;
+}
+template <int R, typename PGT, bool SLICES, int PSI_MODE>
 __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logit_kernel(const View v) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
+    constexpr int ROWS_MAX = site_stage_rows(R);
     static_assert(SITE_TILE <= 64, "per-lane site masks are 64-bit");
+    static_assert(PSI_MODE != PSI_F32 || std::is_same<PGT, float>::value, "FP32 psi feeds the FP32 sampler");
     extern __shared__ __align__(16) unsigned char site_smem[];
     PGT (*arg_s)[CHAIN_TILE] = reinterpret_cast<PGT(*)[CHAIN_TILE]>(site_smem);  // psi in, omega_b out
-    // FUSE_PSI: FP64 psi of the current sub-tile, [PSI_SUB][CHAIN_TILE]; a warp only touches its own 32 columns
-    double (*psi_d)[CHAIN_TILE] = reinterpret_cast<double(*)[CHAIN_TILE]>(site_smem + sizeof(PGT) * SITE_TILE * CHAIN_TILE);
+    // PSI_F64: FP64 psi of the tile, [SITE_TILE][CHAIN_TILE]; a warp only touches its own 32 columns
+    unsigned char* sp = site_smem + sizeof(PGT) * SITE_TILE * CHAIN_TILE;
+    double (*psi_d)[CHAIN_TILE] = reinterpret_cast<double(*)[CHAIN_TILE]>(sp);
+    if (PSI_MODE == PSI_F64) sp += SITE_TILE * CHAIN_TILE * sizeof(double);
+    double* wt_s = reinterpret_cast<double*>(sp);                 // [ROWS_MAX][R + 1]: w_ij, y_ij - 1/2
+    int* vp_s = reinterpret_cast<int*>(wt_s + ROWS_MAX * (R + 1));   // visit_ptr[i0 .. i0 + SITE_TILE]
+    uint8_t* cls_s = reinterpret_cast<uint8_t*>(vp_s + SITE_TILE + 4);
     const int tid = threadIdx.x;
     const uint32_t iter = v.ctl->iter;
     const bool first = v.ctl->first != 0;
     // FP64 occupancy probabilities: validation build and debug engines (which dump them, OCCU_F_ZPROB)
-    const bool zf64 = std::is_same<PGT, double>::value || v.zprob != nullptr;
+    const bool zf64 = PSI_MODE == PSI_F32 ? false : (std::is_same<PGT, double>::value || v.zprob != nullptr);
     const size_t Cp = v.Cp;
     const int tile = blockIdx.x;
     const int c = blockIdx.y * CHAIN_TILE + tid;
     const int i0 = tile * SITE_TILE;
     const int i1 = min(i0 + SITE_TILE, v.n);
     const uint32_t gc = (uint32_t)(v.chain_offset + c);
+
+    // ---- stage the tile's share of the CSR visit layout: offsets, site classes, and (when they fit) the visit rows ----
+    if (tid <= SITE_TILE) vp_s[tid] = v.visit_ptr[min(i0 + tid, v.n)];
+    if (tid < SITE_TILE) cls_s[tid] = i0 + tid < v.n ? v.site_class[i0 + tid] : (uint8_t)OCCU_SITE_NOT_SURVEYED;
+    const int row0 = v.visit_ptr[i0];
+    const int nrows = v.visit_ptr[i1] - row0;
+    const bool staged = nrows <= ROWS_MAX;
+    if (staged) {
+        for (int idx = tid; idx < nrows * (R + 1); idx += CHAIN_TILE) {
+            const int row = idx / (R + 1), k = idx - row * (R + 1);
+            wt_s[idx] = k < R ? v.W[(size_t)(row0 + row) * R + k] : (double)v.y[row0 + row] - 0.5;
+        }
+    }
+    __syncthreads();
+    // design row of visit vv and y - 1/2 (logit.py:189, 221)
+    auto load_row = [&](int vv, double (&w)[R], double& yk) {
+        if (staged) {
+            const double* rowp = wt_s + (vv - row0) * (R + 1);
+#pragma unroll
+            for (int k = 0; k < R; k++) w[k] = rowp[k];
+            yk = rowp[R];
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) w[k] = v.W[(size_t)vv * R + k];
+            yk = (double)v.y[vv] - 0.5;
+        }
+    };
 
     double al[R];
 #pragma unroll
@@ -91,14 +141,15 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
     // ---- phase 1: z | . ----
     uint64_t zbits = 0ull;   // z of the tile's sites
     uint64_t pend = 0ull;    // sites whose visits get omega_a draws: surveyed and occupied
-    static_assert(SITE_TILE % PSI_SUB == 0, "whole DMMA sub-tiles");
-    for (int ib = i0; ib < i1; ib += PSI_SUB) {
-    if (FUSE_PSI) psi_subtile_dmma(v, ib, tid, c, psi_d);
-    for (int i = ib; i < min(ib + PSI_SUB, i1); i++) {
-        const int cls = v.site_class[i];
+    // psi of the whole tile first: straight into the PG argument tile as FP32 (the only precision production engines use
+    // psi in), or into the FP64 staging tile of a debug engine
+    if (PSI_MODE == PSI_F32) psi_tile_dmma(v, i0, tid, c, reinterpret_cast<float(*)[CHAIN_TILE]>(site_smem));
+    if (PSI_MODE == PSI_F64) psi_tile_dmma(v, i0, tid, c, psi_d);
+    for (int i = i0; i < i1; i++) {
+        const int cls = cls_s[i - i0];
         const size_t off = (size_t)i * Cp + c;
-        const double psi = FUSE_PSI ? psi_d[i - ib][tid] : v.psi[off];
-        if (FUSE_PSI && v.zprob) v.psi[off] = psi;   // debug engines keep psi readable
+        const double psi = PSI_MODE == PSI_F32 ? (double)arg_s[i - i0][tid] : (PSI_MODE == PSI_F64 ? psi_d[i - i0][tid] : v.psi[off]);
+        if (PSI_MODE == PSI_F64 && v.zprob) v.psi[off] = psi;   // debug engines keep psi readable
         int zc;
         if (first) {
             zc = v.z[off];
@@ -111,15 +162,17 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
                 // visit and one division per site; not-surveyed sites have the empty product
                 Philox g;
                 g.init(v.seed, gc, (uint32_t)i, iter, ST_Z);
-                g.refill_rk(v.rk);
+                const int v0 = vp_s[i - i0], v1 = vp_s[i - i0 + 1];
                 if (zf64) {
+                    g.refill_rk(v.rk);
                     double grow = exp(-psi);
                     if (cls == OCCU_SITE_NOT_OBS) {
-                        const int v1 = v.visit_ptr[i + 1];
-                        for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
+                        for (int vv = v0; vv < v1; vv++) {
+                            double w[R], yk;
+                            load_row(vv, w, yk);
                             double lin = 0.0;
 #pragma unroll
-                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            for (int k = 0; k < R; k++) lin += w[k] * al[k];
                             grow *= 1.0 + exp(lin);
                         }
                     }
@@ -130,13 +183,15 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
                 } else {
                     // same probability in FP32 log2 space (MUFU ex2 / lg2): lg = log2(exp(-psi) prod (1 + exp(w alpha)));
                     // an overflowing factor gives lg = +inf and probability 0, its limit
+                    g.refill_rk<PHILOX_FAST_ROUNDS>(v.rk);
                     float lg = -1.4426950408889634f * (float)psi;
                     if (cls == OCCU_SITE_NOT_OBS) {
-                        const int v1 = v.visit_ptr[i + 1];
-                        for (int vv = v.visit_ptr[i]; vv < v1; vv++) {
+                        for (int vv = v0; vv < v1; vv++) {
+                            double w[R], yk;
+                            load_row(vv, w, yk);
                             double lin = 0.0;
 #pragma unroll
-                            for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
+                            for (int k = 0; k < R; k++) lin += w[k] * al[k];
                             lg += f_lg2(1.0f + f_ex2(1.4426950408889634f * (float)lin));
                         }
                     }
@@ -151,9 +206,8 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
         }
         zbits |= (uint64_t)zc << (i - i0);
         if (cls != OCCU_SITE_NOT_SURVEYED && zc) pend |= 1ull << (i - i0);
-        arg_s[i - i0][tid] = (PGT)psi;
+        if (PSI_MODE != PSI_F32) arg_s[i - i0][tid] = (PGT)psi;
     }
-    }  // sub-tiles
     __syncwarp();   // phase 2 reads the warp's 32 columns of arg_s across lanes
 
     // ---- phase 2: PG draws ----
@@ -170,7 +224,7 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
     bool have = false, is_visit = false;
     typename PGSel<PGT>::Task task;
     Philox g;
-    double wv[R];  // design row of the visit being drawn (kept from the fetch to the commit)
+    double wv[R], wy = 0.0;  // design row and y - 1/2 of the visit being drawn (kept from the fetch to the commit)
 #pragma unroll
     for (int k = 0; k < R; k++) wv[k] = 0.0;
     for (;;) {
@@ -183,17 +237,15 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
             if (vv >= vend && pend) {   // next occupied surveyed site of this lane's chain
                 const int s = __ffsll((long long)pend) - 1;
                 pend &= pend - 1ull;
-                vv = v.visit_ptr[i0 + s];
-                vend = v.visit_ptr[i0 + s + 1];
+                vv = vp_s[s];
+                vend = vp_s[s + 1];
             }
             if (vv < vend) {
                 cur = vv++;
+                load_row(cur, wv, wy);
                 double lin = 0.0;
 #pragma unroll
-                for (int k = 0; k < R; k++) {
-                    wv[k] = v.W[(size_t)cur * R + k];
-                    lin += wv[k] * al[k];
-                }
+                for (int k = 0; k < R; k++) lin += wv[k] * al[k];
                 carg = (PGT)lin;
                 pelem = (uint32_t)cur;
                 is_visit = true;
@@ -231,7 +283,7 @@ __global__ void __launch_bounds__(CHAIN_TILE, site_min_blocks(R)) site_pass_logi
                 have = false;
                 if (is_visit) {
                     const double om = 0.25 * (double)x;
-                    const double yk = (double)v.y[cur] - 0.5;
+                    const double yk = wy;
                     int idx = 0;
 #pragma unroll
                     for (int a = 0; a < R; a++) {
@@ -358,7 +410,7 @@ struct SiteDebug {
 // No rejection loops (inverse-CDF draws), so the lanes stay in lock-step over the sites of the tile.
 //
 // Production precision (F64 = false, nothing injected): the latent draws and the occupancy probability run in FP32
-// (normcdff / normcdfinvf; KS tests arbitrate, tests/test_gpu_primitives.py), ONE Philox4x32-7 block serves a site
+// (erfc_pos_fast / ndtri_fast; KS tests arbitrate, tests/test_gpu_primitives.py), ONE Philox4x32-7 block serves a site
 // (words: z | omega_b | two for the eps normal) and one block serves four visits of a site; psi = [X K] theta is formed
 // here on the FP64 tensor pipe (FUSE_PSI, as in the logit pass) and only eps, d and z cross HBM (25 B per site and
 // chain; omega_b = d + eps is materialised on request).  Debug / validation engines keep FP64 everywhere, one
@@ -367,7 +419,7 @@ struct SiteDebug {
 template <int R, bool F64, bool FUSE_PSI>
 __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
-    __shared__ __align__(16) double psi_d[FUSE_PSI ? PSI_SUB : 1][CHAIN_TILE];
+    __shared__ __align__(16) float psi_s[FUSE_PSI ? SITE_TILE : 1][CHAIN_TILE];   // production engines only (FP32 psi)
     const int tid = threadIdx.x;
     const int c = blockIdx.y * CHAIN_TILE + tid;
     const int tile = blockIdx.x;
@@ -388,13 +440,11 @@ __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kern
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
-    for (int ib = i0; ib < i1; ib += PSI_SUB) {
-    if (FUSE_PSI) psi_subtile_dmma(v, ib, tid, c, psi_d);
-    for (int i = ib; i < min(ib + PSI_SUB, i1); i++) {
+    if (FUSE_PSI) psi_tile_dmma(v, i0, tid, c, psi_s);
+    for (int i = i0; i < i1; i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
-        const double lp = FUSE_PSI ? psi_d[i - ib][tid] : v.psi[off];   // x_i beta + K_i eta
-        if (FUSE_PSI && v.zprob) v.psi[off] = lp;                       // debug engines keep psi readable
+        const double lp = FUSE_PSI ? (double)psi_s[i - i0][tid] : v.psi[off];   // x_i beta + K_i eta
         const double ep = v.eps[off];
         const double loc = lp + ep;
         const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
@@ -476,14 +526,16 @@ __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kern
                     zc = 1;
                 } else {
                     // z = 1 with probability num / (den + num), num = Phi(loc) prod_j Phi(-w_ij alpha), den = Phi(-loc)
-                    float num = normcdff((float)loc);
-                    const float den = normcdff(-(float)loc);
+                    float num, den;
+                    phi_pair_fast((float)loc, num, den);
                     if (cls == OCCU_SITE_NOT_OBS) {
                         for (int vv = v0; vv < v1; vv++) {
                             double lin = 0.0;
 #pragma unroll
                             for (int k = 0; k < R; k++) lin += v.W[(size_t)vv * R + k] * al[k];
-                            num *= normcdff(-(float)lin);
+                            float ph, phn;
+                            phi_pair_fast((float)lin, ph, phn);
+                            num *= phn;
                         }
                     }
                     const float u = fmaf(__uint2float_rz(wz), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
@@ -492,34 +544,34 @@ __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kern
                 v.z[off] = (uint8_t)zc;
             }
             if (cls != OCCU_SITE_NOT_SURVEYED && zc) {
-                for (int vg = v0; vg < v1; vg += 4) {
-                    Philox ga;
-                    ga.init(v.seed, gc, (uint32_t)vg, iter, ST_OMEGA_A);
-                    ga.refill_rk<PHILOX_FAST_ROUNDS>(v.rk);
-                    ga.have = 0;
-                    const uint32_t wd[4] = {ga.buf[0], ga.buf[1], ga.buf[2], ga.buf[3]};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int vv = vg + j;
-                        if (vv < v1) {
-                            double w[R];
-                            double lin = 0.0;
-#pragma unroll
-                            for (int k = 0; k < R; k++) {
-                                w[k] = v.W[(size_t)vv * R + k];
-                                lin += w[k] * al[k];
-                            }
-                            const double oma = truncnorm_word_f32(lin, v.y[vv] == 1, wd[j], ga);
-                            int idx = 0;
-#pragma unroll
-                            for (int a = 0; a < R; a++) {
-#pragma unroll
-                                for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
-                            }
-#pragma unroll
-                            for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
-                        }
+                Philox ga;
+                uint32_t wd0 = 0u, wd1 = 0u, wd2 = 0u, wd3 = 0u;
+#pragma unroll 1
+                for (int vv = v0; vv < v1; vv++) {
+                    const int j = (vv - v0) & 3;
+                    if (j == 0) {   // one Philox block per four visits of the site
+                        ga.init(v.seed, gc, (uint32_t)vv, iter, ST_OMEGA_A);
+                        ga.refill_rk<PHILOX_FAST_ROUNDS>(v.rk);
+                        ga.have = 0;
+                        wd0 = ga.buf[0]; wd1 = ga.buf[1]; wd2 = ga.buf[2]; wd3 = ga.buf[3];
                     }
+                    const uint32_t word = j == 0 ? wd0 : (j == 1 ? wd1 : (j == 2 ? wd2 : wd3));
+                    double w[R];
+                    double lin = 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; k++) {
+                        w[k] = v.W[(size_t)vv * R + k];
+                        lin += w[k] * al[k];
+                    }
+                    const double oma = truncnorm_word_f32(lin, v.y[vv] == 1, word, ga);
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < R; a++) {
+#pragma unroll
+                        for (int b = 0; b <= a; b++) acc[idx++] += w[a] * w[b];  // probit.py:233
+                    }
+#pragma unroll
+                    for (int a = 0; a < R; a++) acc[NA + a] += w[a] * oma;  // probit.py:234
                 }
             }
             omb = truncnorm_word_f32(loc, zc == 1, wb, g);   // probit.py:196-209
@@ -530,7 +582,6 @@ __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : 6) site_pass_probit_kern
         v.eps[off] = ep_new;
         v.kd[off] = omb - ep_new;  // d: right-hand-side vector of both the eta and the beta systems
     }
-    }  // sub-tiles
 #pragma unroll
     for (int k = 0; k < NV; k++) v.apart[((size_t)tile * NV + k) * Cp + c] = acc[k];
 }

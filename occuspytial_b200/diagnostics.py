@@ -78,8 +78,21 @@ def hdi(x, prob=0.94):
     return float(x[i]), float(x[i + k])
 
 
-def summary_frame(data, max_lag=None):
-    """pandas.DataFrame with arviz-like columns for ``{name: (chains, draws[, dim])}``."""
+def pooled_moments(summ, draws):
+    """Pooled mean and standard deviation (ddof = 1) of all draws from the per-chain blocks (equal chain lengths)."""
+    chains = summ.shape[0]
+    mean = summ[:, 0].mean()
+    m2 = summ[:, 1].sum() + draws * ((summ[:, 0] - mean) ** 2).sum()
+    total = chains * draws
+    return float(mean), float(np.sqrt(m2 / (total - 1))) if total > 1 else float('nan')
+
+
+def summary_frame(data, max_lag=None, summaries=None):
+    """pandas.DataFrame with arviz-like columns for ``{name: (chains, draws[, dim])}``.
+
+    ``summaries``: optional per-chain summary blocks ``{name: (chains, dim, 6 + L + 1)}`` (device-computed, possibly
+    covering more chains than ``data`` holds locally); mean, sd, mcse_mean, ess_bulk and r_hat are then derived from
+    them, only the HDI is taken from the draws in ``data``."""
     import pandas as pd
     rows, index = [], []
     for name, arr in data.items():
@@ -88,11 +101,16 @@ def summary_frame(data, max_lag=None):
             arr = arr[:, :, None]
         chains, draws, dim = arr.shape
         L = min(draws - 1, 250) if max_lag is None else max_lag
+        blocks = None if summaries is None or name not in summaries else np.asarray(summaries[name])
         for k in range(dim):
             x = arr[:, :, k]
-            summ = summaries_from_draws(x, L) if draws > 3 else None
-            mean, sd = x.mean(), x.std(ddof=1) if x.size > 1 else np.nan
-            lo, hi = hdi(x)
+            if blocks is not None:
+                summ = blocks[:, k, :]
+                mean, sd = pooled_moments(summ, draws)
+            else:
+                summ = summaries_from_draws(x, L) if draws > 3 else None
+                mean, sd = x.mean(), x.std(ddof=1) if x.size > 1 else np.nan
+            lo, hi = hdi(x) if x.size else (np.nan, np.nan)
             if summ is not None:
                 n_eff = ess(summ, draws)
                 rhat = split_rhat(summ, draws) if draws >= 4 else np.nan

@@ -35,7 +35,9 @@ class DeviceEngine:
     """
 
     def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False,
-                 gram_int8=False):
+                 gram_int8=False, workspace=None):
+        import time as _time
+        t_begin = _time.perf_counter()
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
@@ -84,12 +86,19 @@ class DeviceEngine:
             self._host = [np.ascontiguousarray(problem[k], dtype=np.float64) for k in ('a_mu', 'a_prec', 'b_mu', 'b_prec')]
             P.a_mu, P.a_prec, P.b_mu, P.b_prec = (a.ctypes.data for a in self._host)
             self._problem = P
+            t_upload = _time.perf_counter()
             nbytes = self.lib.occu_workspace_bytes(C.byref(P))
             if nbytes == 0:
                 _lib.check(-1, 'occu_workspace_bytes')
-            # allocated (and later freed) in the context of the engine's stream: it is the only stream that touches it
-            with torch.cuda.stream(self.stream):
-                self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            # The workspace is caller-provided memory (include/occu_b200.h): a sampler hands the block of its previous
+            # run back in (`workspace=`) so that repeated sample() calls do not go through cudaMalloc again.  A fresh one
+            # is allocated in the context of the engine's stream, the only stream that touches it.
+            if workspace is not None and workspace.device == self.device and workspace.numel() >= nbytes + 256:
+                self.workspace = workspace
+            else:
+                with torch.cuda.stream(self.stream):
+                    self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            t_alloc = _time.perf_counter()
             base = (self.workspace.data_ptr() + 255) // 256 * 256
             handle = C.c_void_p()
             _lib.check(self.lib.occu_create(C.byref(P), base, nbytes, self.stream.cuda_stream, C.byref(handle)),
@@ -97,6 +106,8 @@ class DeviceEngine:
             self.handle = handle
             self.stream.synchronize()
             del dev  # the engine copied the problem into its workspace
+            t_end = _time.perf_counter()
+            self.setup_seconds = {'upload': t_upload - t_begin, 'alloc': t_alloc - t_upload, 'create': t_end - t_alloc}
 
     # ---- state ---------------------------------------------------------------------------------
     def _field_shape(self, field):
@@ -128,14 +139,32 @@ class DeviceEngine:
         return out
 
     def set_start(self, start):
-        """start: dict of chain-major arrays alpha (C, r), beta (C, p), tau (C,), eta (C, q|n)[, eps (C, n)]."""
-        _lib.check(self.lib.occu_reset(self.handle, self.stream.cuda_stream), 'occu_reset')
-        self.set_field(_lib.F_ALPHA, start['alpha'])
-        self.set_field(_lib.F_BETA, start['beta'])
-        self.set_field(_lib.F_TAU, start['tau'])
-        self.set_field(_lib.F_ETA, start['eta'])
+        """start: dict of chain-major arrays alpha (C, r), beta (C, p), tau (C,), eta (C, q|n)[, eps (C, n)].
+
+        The fields are packed into one pinned host buffer and cross PCIe in a single copy; the engine scatters them
+        into its chain-minor state from device pointers into that block."""
+        torch = self.torch
+        fields = [(_lib.F_ALPHA, 'alpha'), (_lib.F_BETA, 'beta'), (_lib.F_TAU, 'tau'), (_lib.F_ETA, 'eta')]
         if self.model == 'probit_rsr':
-            self.set_field(_lib.F_EPS, start['eps'])
+            fields.append((_lib.F_EPS, 'eps'))
+        parts, offsets, off = [], [], 0
+        for field, name in fields:
+            arr = np.broadcast_to(np.asarray(start[name], dtype=np.float64), (self.chains,) + self._field_shape(field))
+            parts.append(arr)
+            offsets.append(off)
+            off += arr.size
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            host = torch.empty(off, dtype=torch.float64, pin_memory=True)
+            hv = host.numpy()
+            for arr, o in zip(parts, offsets):
+                hv[o:o + arr.size] = arr.reshape(-1)
+            dev = host.to(self.device, non_blocking=True)
+            self.h2d_bytes += off * 8
+            _lib.check(self.lib.occu_reset(self.handle, self.stream.cuda_stream), 'occu_reset')
+            for (field, _), o in zip(fields, offsets):
+                _lib.check(self.lib.occu_set_field(self.handle, field, dev.data_ptr() + 8 * o, self.stream.cuda_stream),
+                           'occu_set_field')
+            self.stream.synchronize()
 
     # ---- sampling ------------------------------------------------------------------------------
     def alloc_record(self, capacity):
@@ -177,6 +206,23 @@ class DeviceEngine:
         """Wait for everything enqueued on this engine; returns the number of failed chains."""
         with self.torch.cuda.device(self.device):
             return _lib.check(self.lib.occu_finish(self.handle, self.stream.cuda_stream), 'occu_finish')
+
+    def chain_summaries(self, record, draws, max_lag):
+        """Per-chain summary blocks of the recorded draws, computed where the draws are: {name: device tensor
+        (chains, dim, 6 + max_lag + 1)} with {mean, M2, split-half means / M2s, autocovariances 0..max_lag}
+        (occu_chain_summaries).  ``record`` must hold exactly ``draws`` draws per chain (capacity == draws)."""
+        torch = self.torch
+        out = {}
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            for name, rec in record.items():
+                dim = rec.shape[2] if rec.dim() == 3 else 1
+                assert rec.shape[1] == draws
+                t = torch.empty((self.chains, dim, 6 + max_lag + 1), dtype=torch.float64, device=self.device)
+                _lib.check(self.lib.occu_chain_summaries(rec.data_ptr(), self.chains, int(draws), int(dim), int(max_lag),
+                                                         t.data_ptr(), self.stream.cuda_stream), 'occu_chain_summaries')
+                out[name] = t
+            self.stream.synchronize()
+        return out
 
     @property
     def launches(self):
@@ -237,11 +283,15 @@ class DeviceEngine:
                                                      self.stream.cuda_stream), 'occu_debug_site_half')
             self.stream.synchronize()
 
-    def close(self):
+    def close(self, keep_workspace=False):
+        """Destroy the engine; ``keep_workspace=True`` returns the workspace tensor for reuse by a later engine."""
+        ws = None
         if getattr(self, 'handle', None) is not None:
             self.lib.occu_destroy(self.handle)
             self.handle = None
+            ws = self.workspace if keep_workspace else None
             self.workspace = None
+        return ws
 
     def __del__(self):
         try:

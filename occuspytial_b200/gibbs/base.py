@@ -22,6 +22,11 @@ from .parallel import sample_parallel, shard_bounds, dist_info
 _RECORD_BYTES = 2 << 30
 
 
+def _summary_lag(draws):
+    """Largest autocovariance lag of the per-chain summary blocks (same rule as diagnostics.summary_frame)."""
+    return int(min(draws - 1, 250))
+
+
 def _check_visits_match(w_ptr, y_ptr):
     """W and y must describe the same visits: same surveyed sites, same number of visits per site.  The kernels
     index y with W's visit offsets, so a mismatch would silently misalign every later site (the reference fails
@@ -121,32 +126,51 @@ class GibbsBase:
     # ------------------------------------------------------------------------------------------
     # start values (base.py:188-212), vectorised over chains
     # ------------------------------------------------------------------------------------------
-    def _eta_start(self, chains):
-        eta = self.rng.standard_normal((chains, self.fixed.n))
+    def _eta_start(self, chains, rng=None):
+        rng = self.rng if rng is None else rng
+        eta = rng.standard_normal((chains, self.fixed.n))
         return eta - eta.mean(axis=1, keepdims=True)
 
-    def _draw_start(self, chains):
+    def _draw_start(self, chains, rng=None):
         """Default start values for ``chains`` chains: tau ~ Gamma(.5, 1/tau_rate), alpha ~ N(a_mu, 100 a_prec),
         beta ~ N(b_mu, 100 b_prec) (precision used as covariance, as the reference does), eta per model."""
+        rng = self.rng if rng is None else rng
         f = self.fixed
         La = np.linalg.cholesky(100 * np.asarray(f.a_prec, dtype=np.float64))
         Lb = np.linalg.cholesky(100 * np.asarray(f.b_prec, dtype=np.float64))
         start = {
-            'tau': self.rng.gamma(0.5, 1 / f.tau_rate, size=chains),
-            'eta': self._eta_start(chains),
-            'alpha': np.asarray(f.a_mu) + self.rng.standard_normal((chains, La.shape[0])) @ La.T,
-            'beta': np.asarray(f.b_mu) + self.rng.standard_normal((chains, Lb.shape[0])) @ Lb.T,
+            'tau': rng.gamma(0.5, 1 / f.tau_rate, size=chains),
+            'eta': self._eta_start(chains, rng),
+            'alpha': np.asarray(f.a_mu) + rng.standard_normal((chains, La.shape[0])) @ La.T,
+            'beta': np.asarray(f.b_mu) + rng.standard_normal((chains, Lb.shape[0])) @ Lb.T,
         }
         return start
 
-    def _start_arrays(self, chains, start):
+    def _start_arrays(self, chains, start, rng=None):
         if start is None:
-            return self._draw_start(chains)
+            return self._draw_start(chains, rng)
         out = {}
         for key in self._start_keys():
             value = np.asarray(start[key], dtype=np.float64)
             out[key] = np.broadcast_to(value, (chains,) + value.shape).copy()
         return out
+
+    _START_BLOCK = 128   # chains per start-value generator
+
+    def _start_arrays_range(self, seed, lo, hi, start):
+        """Start values of the global chains [lo, hi).  Default starts come from one counter-based generator per block
+        of 128 chains, keyed by (seed, block): a shard draws only the blocks it overlaps, and a chain's start value
+        does not depend on how the job is sharded over devices or ranks."""
+        if start is not None:
+            return self._start_arrays(hi - lo, start)
+        B = self._START_BLOCK
+        parts = []
+        for blk in range(lo // B, -(-hi // B)):
+            rng = np.random.Generator(np.random.Philox(key=[seed & (2**64 - 1), blk]))
+            arrays = self._draw_start(B, rng)
+            a, b = max(lo, blk * B) - blk * B, min(hi, (blk + 1) * B) - blk * B
+            parts.append({k: v[a:b] for k, v in arrays.items()})
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
 
     def _start_keys(self):
         return ('alpha', 'beta', 'tau', 'eta')
@@ -207,14 +231,18 @@ class GibbsBase:
         if problem is None:   # flattening the ragged W / y dictionaries is the costly part: once per sampler
             problem = self._problem_arrays()
             self.__dict__['_problem_cache'] = problem
+        import torch
+        key = str(torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)) \
+            if torch.cuda.is_available() else None
+        ws = self.__dict__.get('_ws_cache', {}).pop(key, None)   # the previous run's workspace on this device, if any
         try:
             return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
-                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8)
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8, workspace=ws)
         except EngineError as exc:
             if not (auto and gram_int8 and 'INT8' in str(exc)):
                 raise
             return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
-                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=False)
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=False, workspace=ws)
 
     def step(self):
         """Step through one iteration of the sampler.
@@ -242,97 +270,228 @@ class GibbsBase:
         self.state.z = self._sites_from_engine(engine.get_field(_lib.F_Z, chain=0)[0].astype(np.float64))
         self.state.k = self.state.z - 0.5
 
-    def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None,
-                      pg_fp64=False, gram_int8=None):
-        """All chains of this process in lock-step on one device; returns the list of ``Chain`` views.
+    def _pick_devices(self, device, devices, local_chains):
+        """Devices of a single-process run.  ``device`` pins one; ``devices`` may be a list, an int or 'all'; by default
+        every visible GPU takes part as long as each gets at least 128 chains (the reference's default is all cores,
+        parallel.py:38)."""
+        import torch
+        if device is not None:
+            return [torch.device(device)]
+        count = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        if isinstance(devices, (list, tuple)):
+            return [torch.device(d) if not isinstance(d, int) else torch.device('cuda', d) for d in devices]
+        if count <= 1:
+            return [None]   # DeviceEngine: current device (raises the "no CPU fallback" error when there is none)
+        if devices == 'all':
+            use = count
+        elif isinstance(devices, int):
+            use = max(1, min(devices, count))
+        else:
+            use = max(1, min(count, local_chains // 128))
+        if use == 1:
+            return [None]
+        return [torch.device('cuda', i) for i in range(use)]
 
-        Under torch.distributed the global ``chains`` are sharded contiguously over ranks and only the
-        local shard is run and returned (global chain ids key the Philox streams, so the draws of a
-        chain do not depend on the number of GPUs).
-        """
-        if self._model is None:
-            raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
-        rank, world = dist_info()
-        if device is None and world > 1:
-            import os
-            device = f"cuda:{os.environ.get('LOCAL_RANK', rank)}"   # one process per GPU under torchrun
-        # the same host RNG stream is consumed on every rank: start values and the device seed are
-        # generated for ALL chains and sliced, so that sharding never changes a chain
-        seed = int(self.rng.integers(0, 2**63 - 1))
-        arrays = self._start_arrays(chains, start)
-        lo, hi = shard_bounds(chains, world, rank)
-        local = hi - lo
-        self._last_arrays = None
-        self._last_stats = None
-        if local <= 0:   # more ranks than chains: this rank holds an empty shard
-            dims = {'alpha': self.W[self.W.surveyed[0]].shape[1], 'beta': self.X.shape[1], 'tau': 1}
-            self._last_arrays = {k: np.empty((0, size - burnin) + ((d,) if d > 1 else ())) for k, d in dims.items()}
-            return []
-        arrays = {k: v[lo:hi] for k, v in arrays.items()}
+    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries):
+        """Chains [lo, hi) in lock-step on one device.  Returns (host arrays, summary blocks or None, stats)."""
         import time as _time
+        import torch
+        local = hi - lo
         t_begin = _time.perf_counter()
+        arrays = self._start_arrays_range(seed, lo, hi, start)
+        t_start = _time.perf_counter()
         engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8)
+        summaries = None
         try:
             engine.set_start(self._start_to_engine(arrays))
-            t_setup = _time.perf_counter() - t_begin
-            t_sweep = t_flush = 0.0
+            t_setup = _time.perf_counter()
             draws = size - burnin
             dims = {'alpha': engine.r, 'beta': engine.p, 'tau': 1}
             per_draw = 8 * local * sum(dims.values())
             capacity = int(max(1, min(draws, _RECORD_BYTES // per_draw)))
-            record = engine.alloc_record(capacity)
+            # everything fits one record block (the usual case): its host copy is the result.  Otherwise two blocks
+            # alternate: while the sweep fills one, the other crosses PCIe on a second stream.
+            bufs = [engine.alloc_record(capacity)] + ([engine.alloc_record(capacity)] if capacity < draws else [])
             shapes = {k: (local, draws) + ((d,) if d > 1 else ()) for k, d in dims.items()}
-            # one record block holds every draw (the usual case): its host copy is the result, no staging array
             host = {k: (None if capacity >= draws else np.empty(shp)) for k, shp in shapes.items()}
-            block = int(min(max(1, size // 20), 256))
-            bar = tqdm(total=size, disable=not progressbar, position=pos)
-            done, filled, flushed = 0, 0, 0
+            block = int(min(max(1, size // 20), 256)) if bar is not None else 256
+            copy_stream = torch.cuda.Stream(device=engine.device) if len(bufs) > 1 else None
+            t_flush = 0.0
 
-            def flush():
-                nonlocal filled, flushed, t_flush
-                if not filled:
-                    return
+            def copy_out(rec, filled, flushed, event):
+                nonlocal t_flush
                 t0 = _time.perf_counter()
-                for k, d in dims.items():
-                    part = record[k][:, :filled].cpu().numpy()
-                    engine.d2h_bytes += part.nbytes
-                    if host[k] is None:   # everything fitted in one block: the copy IS the result
-                        host[k] = part.reshape(shapes[k])
+                with torch.cuda.device(engine.device):
+                    if copy_stream is not None:
+                        copy_stream.wait_event(event)
+                        ctx = torch.cuda.stream(copy_stream)
                     else:
-                        host[k][:, flushed:flushed + filled] = part.reshape(host[k][:, flushed:flushed + filled].shape)
-                flushed += filled
-                filled = 0
+                        engine.stream.synchronize()
+                        ctx = torch.cuda.stream(engine.stream)
+                    with ctx:
+                        for k in dims:
+                            part = rec[k][:, :filled].cpu().numpy()
+                            engine.d2h_bytes += part.nbytes
+                            if host[k] is None:   # everything fitted in one block: the copy IS the result
+                                host[k] = part.reshape(shapes[k])
+                            else:
+                                dst = host[k][:, flushed:flushed + filled]
+                                dst[...] = part.reshape(dst.shape)
                 t_flush += _time.perf_counter() - t0
 
-            fails = 0
+            done, filled, flushed, cur = 0, 0, 0, 0
+            pending = None   # a full record block waiting to be copied: (block, filled, flushed offset, event)
             while done < size:
                 step = min(block, size - done)
-                t0 = _time.perf_counter()
                 if done < burnin:
                     step = min(step, burnin - done)
-                    fails = engine.sweep(step)
+                    engine.sweep_enqueue(step)
                 else:
                     step = min(step, capacity - filled)
-                    fails = engine.sweep(step, record, rec_start=filled)
+                    engine.sweep_enqueue(step, bufs[cur], rec_start=filled)
                     filled += step
-                t_sweep += _time.perf_counter() - t0
-                if done >= burnin and filled == capacity:
-                    flush()
                 done += step
-                bar.update(step)
-            flush()
-            bar.close()
+                if pending is not None:      # copy the previous block while the GPU works on the one just enqueued
+                    copy_out(*pending)
+                    pending = None
+                if done >= burnin and filled == capacity and done < size:
+                    ev = torch.cuda.Event()
+                    ev.record(engine.stream)
+                    pending = (bufs[cur], filled, flushed, ev)
+                    flushed += filled
+                    filled = 0
+                    cur = (cur + 1) % len(bufs)
+                if bar is not None:
+                    engine.finish()          # the bar follows the device, not the launch queue
+                    bar.update(step)
+            fails = engine.finish()
+            t_sweep = _time.perf_counter() - t_setup - t_flush
+            if pending is not None:
+                copy_out(*pending)
+            t0 = _time.perf_counter()
+            if want_summaries and len(bufs) == 1 and filled == draws and draws >= 4:
+                summaries = engine.chain_summaries(bufs[0], draws, _summary_lag(draws))
+            t_summ = _time.perf_counter() - t0
+            if filled:
+                ev = torch.cuda.Event()
+                ev.record(engine.stream)
+                copy_out(bufs[cur], filled, flushed, ev)
             if fails:
                 raise RuntimeError(f'Cholesky factorization/solver failed! ({fails} of {local} chains)')
-            self._pull_state(engine)
-            self._last_stats = dict(launches=engine.launches, h2d_bytes=engine.h2d_bytes,
-                                    d2h_bytes=engine.d2h_bytes, chains=local, chain_offset=lo,
-                                    seconds=dict(setup=t_setup, sweeps=t_sweep, flush=t_flush))
+            t0 = _time.perf_counter()
+            if lo == 0:
+                self._pull_state(engine)
+            t_pull = _time.perf_counter() - t0
+            stats = dict(launches=engine.launches, h2d_bytes=engine.h2d_bytes, d2h_bytes=engine.d2h_bytes, chains=local,
+                         chain_offset=lo, device=str(engine.device),
+                         seconds=dict(start_values=t_start - t_begin, setup=t_setup - t_start, sweeps=t_sweep,
+                                      flush=t_flush, summaries=t_summ, pull_state=t_pull, **engine.setup_seconds))
         finally:
-            engine.close()
-        out = ChainViews(host)
-        self.chain = out[0]
+            ws = engine.close(keep_workspace=True)
+            if ws is not None:
+                self.__dict__.setdefault('_ws_cache', {})[str(engine.device)] = ws
+        return host, summaries, stats
+
+    def _run_lockstep(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0, device=None, devices=None,
+                      pg_fp64=False, gram_int8=None):
+        """All chains in lock-step; returns the list of ``Chain`` views of the chains this process ran.
+
+        Single process: the chains are split contiguously over the visible GPUs (``devices``), one engine per device
+        driven from its own host thread -- no launcher needed, like the reference's ``Parallel(n_jobs=-1)``
+        (parallel.py:38).  Under torch.distributed (one process per GPU) the global ``chains`` are sharded over ranks
+        and only the local shard is run and returned.  Either way global chain ids key the Philox streams and the
+        start values, so the draws of a chain do not depend on the number of GPUs; the only exchange is the
+        all-gather of per-chain summary blocks for R-hat / ESS (``PosteriorParameter.summary``).
+        """
+        if self._model is None:
+            raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
+        import time as _time
+        t_call = _time.perf_counter()
+        rank, world = dist_info()
+        # the same host RNG stream is consumed on every rank: one draw for the device seed
+        seed = int(self.rng.integers(0, 2**63 - 1))
+        lo, hi = shard_bounds(chains, world, rank)
+        local = hi - lo
+        draws = size - burnin
+        dims = {'alpha': self.W[self.W.surveyed[0]].shape[1], 'beta': self.X.shape[1], 'tau': 1}
+        self._last_arrays = None
+        self._last_stats = None
+        self._last_summaries = None
+        if world > 1:
+            import os
+            devs = [device if device is not None else f"cuda:{os.environ.get('LOCAL_RANK', rank)}"]
+        else:
+            devs = self._pick_devices(device, devices, local)
+        bar = tqdm(total=size, disable=not progressbar, position=pos) if progressbar else None
+        results = []
+        if local > 0:
+            bounds = [shard_bounds(local, len(devs), i) for i in range(len(devs))]
+            jobs = [(dev, lo + a, lo + b) for dev, (a, b) in zip(devs, bounds) if b > a]
+
+            def job(k):
+                dev, a, b = jobs[k]
+                return self._run_shard(dev, a, b, seed, start, size, burnin, bar if k == 0 else None, pg_fp64, gram_int8,
+                                       want_summaries=True)
+            if len(jobs) == 1:
+                results = [job(0)]
+            else:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(len(jobs)) as pool:   # the C ABI releases the GIL: devices run concurrently
+                    results = list(pool.map(job, range(len(jobs))))
+        if bar is not None:
+            bar.close()
+        if results:
+            host = {k: (results[0][0][k] if len(results) == 1 else np.concatenate([r[0][k] for r in results], axis=0))
+                    for k in dims}
+        else:       # more ranks than chains: this rank holds an empty shard
+            host = {k: np.empty((0, draws) + ((d,) if d > 1 else ())) for k, d in dims.items()}
+        t0 = _time.perf_counter()
+        self._last_summaries = self._gather_summaries(results, chains, local, draws, dims, world)
+        t_gather = _time.perf_counter() - t0
+        if results:
+            stats = [r[2] for r in results]
+            agg = dict(stats[0])
+            for key in ('launches', 'h2d_bytes', 'd2h_bytes', 'chains'):
+                agg[key] = sum(s_[key] for s_ in stats)
+            agg['devices'] = [s_['device'] for s_ in stats]
+            agg['per_device'] = stats
+            agg['seconds'] = dict(agg['seconds'], gather_summaries=t_gather, run_lockstep=_time.perf_counter() - t_call)
+            self._last_stats = agg
+        out = ChainViews(host) if local > 0 else []
+        if local > 0:
+            self.chain = out[0]
         self._last_arrays = host
+        return out
+
+    def _gather_summaries(self, results, chains, local, draws, dims, world):
+        """Global per-chain summary blocks {name: ndarray (chains, dim, 6 + L + 1)} or None.  Device tensors of the
+        local engines are concatenated; under torch.distributed they are all-gathered (NCCL: the blocks never leave
+        the devices until the gathered result is read)."""
+        if draws < 4:
+            return None
+        have = bool(results) and all(r[1] is not None for r in results)
+        if world == 1:
+            if not have:
+                return None
+            return {k: np.concatenate([r[1][k].cpu().numpy() for r in results], axis=0) for k in dims}
+        import torch
+        import torch.distributed as dist
+        from .parallel import allgather_summaries
+        # every rank must agree on whether the collective runs (a rank that flushed in blocks has no device summaries)
+        dev = results[0][1]['tau'].device if have else torch.device('cuda', torch.cuda.current_device()) \
+            if dist.get_backend() == 'nccl' else torch.device('cpu')
+        flag = torch.tensor([1 if (have or local == 0) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return None
+        W = 6 + _summary_lag(draws) + 1
+        out = {}
+        for k, d in dims.items():
+            if have:
+                t = torch.cat([r[1][k] for r in results], dim=0)
+            else:
+                t = torch.zeros((0, d, W), dtype=torch.float64, device=dev)
+            out[k] = allgather_summaries(t, chains).cpu().numpy()
         return out
 
     def _run(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0):
@@ -355,7 +514,8 @@ class GibbsBase:
         progressbar : bool, optional
             Whether to display the progress bar during sampling.
         **engine_kwargs
-            Engine knobs: ``device`` (torch device), ``pg_fp64`` (validation precision for the PG / truncated-
+            Engine knobs: ``device`` (one torch device), ``devices`` (list, count or 'all': GPUs of a single-process
+            run; default: every visible GPU that gets at least 128 chains), ``pg_fp64`` (validation precision for the PG / truncated-
             normal draws), ``gram_int8`` (LogitRSR: exact INT8 slice GEMMs for the Omega-weighted Gram).
 
         Returns
@@ -370,7 +530,8 @@ class GibbsBase:
                                   progressbar=progressbar, **engine_kwargs)
         stacked = getattr(self, '_last_arrays', None)
         if stacked is not None and stacked['tau'].shape[0] == len(samples):
-            return PosteriorParameter.from_arrays(stacked)  # already (chains, draws[, dim]): skip np.stack
+            # already (chains, draws[, dim]): skip np.stack; R-hat / ESS come from the device summary blocks
+            return PosteriorParameter.from_arrays(stacked, summaries=getattr(self, '_last_summaries', None))
         return PosteriorParameter(*samples)
 
     def copy(self):
@@ -378,6 +539,7 @@ class GibbsBase:
         out = type(self).__new__(self.__class__)
         out.__dict__.update(self.__dict__)
         out.__dict__['_engine'] = None
+        out.__dict__.pop('_ws_cache', None)
         seed_seq = self.rng.bit_generator.seed_seq.spawn(1)[0]
         out.__dict__['rng'] = get_generator(seed_seq)
         return out

@@ -97,10 +97,10 @@ class LogitRSRGibbs(LogitICARGibbs):
             del self.fixed.tau_shape
             self.fixed.tau_shape = 0.5 + 0.5 * self.fixed.q
 
-    def _eta_start(self, chains):
-        """logit.py:462-466: eta ~ N(0, 25 I_q).  The base-class draw is still consumed, as in the reference."""
-        super()._eta_start(1)
-        return self.rng.normal(scale=5, size=(chains, self.fixed.q))
+    def _eta_start(self, chains, rng=None):
+        """logit.py:462-466: eta ~ N(0, 25 I_q)."""
+        rng = self.rng if rng is None else rng
+        return rng.normal(scale=5, size=(chains, self.fixed.q))
 
     def _spatial_from_eta(self, eta):
         return self.fixed.K @ eta

@@ -49,13 +49,14 @@ class ProbitRSRGibbs(GibbsBase):
             del self.fixed.tau_shape
             self.fixed.tau_shape = 0.5 + 0.5 * self.fixed.q
 
-    def _eta_start(self, chains):
-        super()._eta_start(1)
-        return self.rng.normal(scale=5, size=(chains, self.fixed.q))
+    def _eta_start(self, chains, rng=None):
+        rng = self.rng if rng is None else rng
+        return rng.normal(scale=5, size=(chains, self.fixed.q))
 
-    def _draw_start(self, chains):
-        start = super()._draw_start(chains)
-        start['eps'] = self.rng.standard_normal((chains, self.fixed.n))   # probit.py:159
+    def _draw_start(self, chains, rng=None):
+        rng = self.rng if rng is None else rng
+        start = super()._draw_start(chains, rng)
+        start['eps'] = rng.standard_normal((chains, self.fixed.n))   # probit.py:159
         return start
 
     def _start_keys(self):

@@ -33,12 +33,20 @@ class PosteriorParameter:
 
     def __init__(self, *chains):
         self.data = self._create_inference_data(chains)
+        self.summaries = None
 
     @classmethod
-    def from_arrays(cls, arrays):
-        """Build from already stacked arrays ``{name: (chains, draws[, dim])}`` (no per-chain objects)."""
+    def from_arrays(cls, arrays, summaries=None):
+        """Build from already stacked arrays ``{name: (chains, draws[, dim])}`` (no per-chain objects).
+
+        ``summaries``: per-chain summary blocks ``{name: (all chains, dim, 6 + L + 1)}`` computed on the device(s)
+        where the draws were recorded and, in a multi-process run, all-gathered over the ranks
+        (include/occu_b200.h: occu_chain_summaries; gibbs/parallel.py: allgather_summaries).  ``summary`` then takes
+        mean, sd, MCSE, ESS and split R-hat from them -- over ALL chains of the job, also those whose draws live in
+        another process -- without touching the draws."""
         self = cls.__new__(cls)
         self.data = self._wrap(dict(arrays))
+        self.summaries = summaries
         return self
 
     @staticmethod
@@ -65,7 +73,7 @@ class PosteriorParameter:
         if az is not None:
             return az.summary(self.data)
         from .diagnostics import summary_frame
-        return summary_frame({name: var.data for name, var in self.data.items()})
+        return summary_frame({name: var.data for name, var in self.data.items()}, summaries=self.summaries)
 
     def plot_trace(self, **kwargs):
         """Plot density and samples values of parameters (arviz.plot_trace)."""

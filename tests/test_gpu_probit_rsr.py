@@ -156,7 +156,10 @@ def test_probit_full_size_invariants():
     omega, eps1 = eng.get_field(_lib.F_OMEGA), eng.get_field(_lib.F_EPS)
     cls = s.fixed.site_class
     assert set(np.unique(z)) <= {0, 1} and np.all(z[:, cls == 2] == 1)
-    assert np.all((omega > 0) == (z == 1))
+    # omega_b = d + eps is re-formed from the stored pair on a production engine: the sign is that of the draw except for
+    # a handful of values at the FP64 rounding level of |eps|
+    assert np.all(omega[z == 1] > -1e-12) and np.all(omega[z == 0] < 1e-12)
+    assert ((omega > 0) != (z == 1)).mean() < 1e-6
     loc = psi0 + eps0
     ok = np.abs(loc) < 5                            # away from the far tail the PIT is numerically clean in FP64
     pos = (z == 1) & ok
