@@ -326,8 +326,8 @@ def run_b200(args):
         dmma_info = {'kernel': "dgemm::gemm_tn_kernel (hand-written FP64 DMMA Gram, gram='dmma' path)", 'ms_per_launch': g_ms,
                      'step_ms_with_this_path': sum(v[0] / max(v[1], 1) for v in k2.values())}
 
-    # ---- end to end through the public API: host data in, host draws out.  ONE timed call of sampler.sample() after one
-    # short untimed call of the same API (first-call costs: lazy kernel loading, allocator); the timed call includes its own
+    # ---- end to end through the public API: host data in, host draws out.  Timed calls of sampler.sample() after one short
+    # untimed call of the same API (first-call costs: lazy kernel loading, allocator); every timed call includes its own
     # problem upload, start values, every iteration, the device summary blocks and the D2H of the draws ----
     e2e = None
     if not args.no_e2e:
@@ -338,15 +338,21 @@ def run_b200(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, **kw)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        st = sampler._last_stats
-        if world > 1:   # a call is as slow as its slowest rank
-            t = torch.tensor([dt], dtype=torch.float64, device='cuda')
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        calls = []
+        for _ in range(3):      # three timed calls, every one reported; the headline is their MEDIAN
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            post = sampler.sample(args.steps + args.warmup, burnin=args.warmup, **kw)
+            torch.cuda.synchronize()
+            one = time.perf_counter() - t0
+            if world > 1:   # a call is as slow as its slowest rank
+                t = torch.tensor([one], dtype=torch.float64, device='cuda')
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                one = float(t.item())
+            calls.append((one, sampler._last_stats))
+        dt, st = sorted(calls, key=lambda c_: c_[0])[1]
         iters = args.steps + args.warmup
         assert post['tau'].shape == (local, args.steps)
         summ = sampler._last_summaries
@@ -356,11 +362,12 @@ def run_b200(args):
             dist.all_reduce(h2d)
         e2e = {'value': chains_total * iters / dt, 'unit': 'chain-iterations/s',
                'h2d_bytes_per_step': float(h2d[0]) / iters, 'd2h_bytes_per_step': float(h2d[1]) / iters,
-               'seconds': dict(st.get('seconds', {}), total=dt),
+               'seconds': dict(st.get('seconds', {}), total=dt), 'timed_calls_s': [c_[0] for c_ in calls],
                'r_hat_tau_from_device_summaries': float(post.summary.loc['tau', 'r_hat']),
-               'note': f'one timed sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) call, wall clock incl. '
-                       'problem upload, start values, all iterations, per-chain summary blocks (all-gathered over the ranks) '
-                       'and the copy of the recorded draws to host; one short untimed call of the same API before it'}
+               'note': f'median of three timed sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) calls (all three '
+                       'listed in timed_calls_s), wall clock incl. problem upload, start values, all iterations, per-chain '
+                       'summary blocks (all-gathered over the ranks) and the copy of the recorded draws to host; one short '
+                       'untimed call of the same API before them'}
 
     if rank != 0:
         if world > 1:

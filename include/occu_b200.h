@@ -120,6 +120,9 @@ void occu_destroy(occu_engine_t* eng);
 /* Start values (GibbsBase._initialize_posterior_state, base.py:188-197; logit.py:468-476; probit.py:162-171). */
 int occu_set_field(occu_engine_t* eng, int field, const void* src_chain_major, void* stream);
 int occu_get_field(occu_engine_t* eng, int field, void* dst_chain_major, void* stream);
+/* One chain's copy of a field, [dim]: what the reference exposes as `sampler.state.<name>` after a run (base.py:15-27,
+ * 236-239) without gathering the other chains. */
+int occu_get_field_chain(occu_engine_t* eng, int field, int chain, void* dst, void* stream);
 
 /* Re-arm the engine at iteration 0 with z reset from the data (start of GibbsBase._run, base.py:226). */
 int occu_reset(occu_engine_t* eng, void* stream);

@@ -45,6 +45,7 @@ SIGNATURES = {
     'occu_destroy': (None, [C.c_void_p]),
     'occu_set_field': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_get_field': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'occu_get_field_chain': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_reset': (C.c_int, [C.c_void_p, C.c_void_p]),
     'occu_sweep': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'occu_sweep_enqueue': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

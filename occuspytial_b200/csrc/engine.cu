@@ -258,11 +258,21 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
         if (!use_old) {
             const size_t smem_w = icarw_smem_bytes(v.bw, v.p);
             size_t& configured_w = e->smem_configured[0];   // per engine: the attribute is per device
-            if (smem_w > configured_w) {
-                CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-                configured_w = smem_w;
+            const int nt = icarw_nt(v.bw);
+            const bool grow = smem_w > configured_w;
+            switch (nt <= 8 ? nt : 0) {
+#define CASE(NT)                                                                                                            \
+    case NT:                                                                                                                \
+        if (grow) CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_warp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); \
+        solve_logit_icar_warp_kernel<NT><<<v.Cp, ICARW_THREADS, smem_w, st>>>(v, dbg, rb, rt, cap);                          \
+        break;
+                CASE(2) CASE(4) CASE(6) CASE(8)
+                default:
+                    if (grow) CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+                    solve_logit_icar_warp_kernel<0><<<v.Cp, ICARW_THREADS, smem_w, st>>>(v, dbg, rb, rt, cap);
+#undef CASE
             }
-            solve_logit_icar_warp_kernel<<<v.Cp, ICARW_THREADS, smem_w, st>>>(v, dbg, rb, rt, cap);
+            if (grow) configured_w = smem_w;
             e->launches++;
             PROF_MARK(e, KC_COUNT, st);
             CUDA_OK(cudaGetLastError());
@@ -308,6 +318,12 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     PROF_MARK(e, KC_COUNT, st);
     CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <typename T>
+__global__ void gather_chain_kernel(const T* __restrict__ src, T* __restrict__ dst, int chain, int Cp, int d) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < d) dst[e] = src[(size_t)e * Cp + chain];
 }
 
 extern "C" {
@@ -573,6 +589,22 @@ int occu_get_field(occu_engine_t* e, int field, void* dst, void* stream) {
     dim3 grid((v.Cp + 31) / 32, (d + 31) / 32), block(32, 8);
     if (u8) to_chain_major_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)ptr, (uint8_t*)dst, v.C, v.Cp, d);
     else to_chain_major_kernel<double><<<grid, block, 0, st>>>((const double*)ptr, (double*)dst, v.C, v.Cp, d);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_get_field_chain(occu_engine_t* e, int field, int chain, void* dst, void* stream) {
+    if (!e || !dst) return set_err("null argument");
+    if (chain < 0 || chain >= e->v.C) return set_err("chain index out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    void* ptr; int d, u8;
+    if (field_info(e, field, &ptr, &d, &u8)) return -1;
+    if (field == OCCU_F_OMEGA && materialise_omega(e, st)) return -1;
+    if (field == OCCU_F_PSI && fuse_psi(e) && !e->debug && launch_psi_gemm(e, st)) return -1;
+    const View& v = e->v;
+    if (u8) gather_chain_kernel<uint8_t><<<(d + 255) / 256, 256, 0, st>>>((const uint8_t*)ptr, (uint8_t*)dst, chain, v.Cp, d);
+    else gather_chain_kernel<double><<<(d + 255) / 256, 256, 0, st>>>((const double*)ptr, (double*)dst, chain, v.Cp, d);
     e->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

@@ -33,11 +33,32 @@
 // ------------------------------------------------------------------------------------------------
 constexpr int ICARW_THREADS = 32;
 
-__host__ __device__ inline int icarw_nt(int bw) { return (bw + 8 + 7) / 8; }
+// window tiles per side: the smallest compiled instance (2, 4, 6, 8: fully unrolled tile loops, constant shared-memory
+// offsets) that covers bw + 8 rows, else the exact count with run-time loops (template argument 0)
+__host__ __device__ inline int icarw_nt_needed(int bw) { return (bw + 8 + 7) / 8; }
+__host__ __device__ inline int icarw_nt(int bw) {
+    const int need = icarw_nt_needed(bw);
+    return need <= 8 ? (need + 1) / 2 * 2 : need;
+}
 __host__ __device__ inline int icarw_wp(int nt) { return (nt & 1) ? 8 * nt : 8 * nt + 8; }   // panel pitch = 8 mod 16 doubles
+__host__ __device__ inline int icarw_w1p(int bw) { return (bw + 1 + 1) / 2 * 2 + 2; }         // staged band row pitch (doubles)
+// shared-memory layout (doubles): region A = window tiles (forward) / x ring + block sums + two staged factor blocks
+// (backward) | panel | forward residuals | one staged group of entering rows | beta system
+__host__ __device__ inline size_t icarw_region_a(int nt, int bw) {
+    const size_t tiles = (size_t)nt * (nt + 1) / 2 * 64, back = 3 * 8 * (size_t)nt + 32 + 2 * (8 * (size_t)icarw_w1p(bw) + 32);
+    return tiles > back ? tiles : back;
+}
 static size_t icarw_smem_bytes(int bw, int p) {
     const size_t nt = icarw_nt(bw), W = 8 * nt, Wp = icarw_wp((int)nt);
-    return (nt * (nt + 1) / 2 * 64 + 8 * Wp + 2 * W + 3 * W + 8 * 4 + (size_t)p * p + 5 * (size_t)p) * sizeof(double);
+    return (icarw_region_a((int)nt, bw) + 8 * Wp + 2 * W + (8 * (size_t)icarw_w1p(bw) + 32) + (size_t)p * p + 5 * (size_t)p) *
+           sizeof(double);
+}
+
+// 8-byte cp.async with zero fill when `ok` is false: lands while the block step in between runs
+__device__ __forceinline__ void icarw_cp8(double* dst, const double* src, bool ok) {
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(src), "r"(bytes));
 }
 
 __device__ __forceinline__ double warp_sum(double val) {
@@ -46,22 +67,27 @@ __device__ __forceinline__ double warp_sum(double val) {
     return val;
 }
 
+template <int NT_T>
 __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(const View v, const SolveDebug dbg, double* rec_beta,
                                                                               double* rec_tau, int rec_capacity) {
     extern __shared__ __align__(16) double icw_sm[];
     const int c = blockIdx.x, lane = threadIdx.x, T = ICARW_THREADS;
     const int g = lane >> 2, t4 = lane & 3;
     const int n = v.n, n4 = round_up_dev(v.n, 4), p = v.p, w = v.bw, W1 = v.bw + 1;
-    const int NT = icarw_nt(w), W = 8 * NT, Wp = icarw_wp(NT);
+    const int NT = NT_T > 0 ? NT_T : icarw_nt(w), W = 8 * NT, Wp = icarw_wp(NT);
+    const int W1p = icarw_w1p(w);
     const int n8 = round_up_dev(n, 8);
     const size_t Cp = v.Cp;
     const HParams* hp = v.hp;
-    double* Ts = icw_sm;                          // [NT (NT + 1) / 2][8][8]  window tiles, pair (a, b), a >= b
-    double* Ps = Ts + NT * (NT + 1) / 2 * 64;     // [8][Wp]  panel, column-major: Ps[col][window row]
-    double* rhs = Ps + 8 * Wp;                    // [2][W]   forward residuals of b and 1, by window row
-    double* xr = rhs + 2 * W;                     // [3][W]   backward: ring of solved x, zv, m by (matrix row mod W)
+    const int stg_sz = 8 * W1p + 32;              // 8 staged band rows + 4 x 8 scalars
+    double* Ts = icw_sm;                          // [NT (NT + 1) / 2][8][8]  window tiles, pair (a, b), a >= b   (forward)
+    double* xr = icw_sm;                          // [3][W]   backward: ring of solved x, zv, m by (matrix row mod W)
     double* Ss = xr + 3 * W;                      // [8][4]   backward: block sums
-    double* small_S = Ss + 32;                    // [p][p]   beta system
+    double* stgB = Ss + 32;                       // [2][stg_sz]  backward: staged factor blocks
+    double* Ps = icw_sm + icarw_region_a(NT, w);  // [8][Wp]  panel, column-major: Ps[col][window row]
+    double* rhs = Ps + 8 * Wp;                    // [2][W]   forward residuals of b and 1, by window row
+    double* stg = rhs + 2 * W;                    // [stg_sz] forward: staged entering rows
+    double* small_S = stg + stg_sz;               // [p][p]   beta system
     double* small_b = small_S + p * p;
     double* small_x = small_b + p;
     double* small_t = small_x + p;
@@ -141,33 +167,62 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
     }
     __syncwarp();
 
-    // Lambda[i][k] (identity beyond n)
-    auto lam = [&](int i, int k) -> double {
-        const int hi = max(i, k), d = hi - min(i, k);
+    // ---- entering rows: the 8 band rows of Q, omega and b of group `grp8 / 8` -> staging buffer `buf` (cp.async; the
+    //      copies land while the block step in between runs) ----
+    auto stage_rows = [&](int base) {
+        double* dst = stg;
+        for (int idx = lane; idx < 8 * W1; idx += T) {
+            const int rr = idx / W1, d = idx - rr * W1;
+            const int i = base + rr;
+            const bool okk = i < n && d <= i;
+            icarw_cp8(dst + rr * W1p + d, okk ? v.Qband + (size_t)i * W1 + d : v.Qband, okk);
+        }
+        if (lane < 16) {
+            const int rr = lane & 7, i = base + rr;
+            const double* srcv = lane < 8 ? om_c : xs;
+            icarw_cp8(dst + 8 * W1p + (lane < 8 ? 0 : 8) + rr, i < n ? srcv + i : srcv, i < n);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    // Lambda[i][k] for a staged row i = base + rr (identity beyond n); k may lie on either side of i
+    auto lam_staged = [&](const double* sb, int base, int i, int k) -> double {
+        // the staged rows are base .. base + 7: an element (i, k) with k > i is Lambda[k][i], available when k is staged too
+        int hi = i, lo = k;
+        if (k > i) {
+            hi = k;
+            lo = i;
+        }
+        const int d = hi - lo;
         if (hi >= n) return d == 0 ? 1.0 : 0.0;
         if (d > w) return 0.0;
-        double val = tau * v.Qband[(size_t)hi * W1 + d];
-        if (d == 0) val += om_c[hi];
+        double val = tau * sb[(hi - base) * W1p + d];
+        if (d == 0) val += sb[8 * W1p + (hi - base)];
         return val;
     };
-    // tile (a, b), a >= b: rows = matrix rows ra .. ra + 7, columns = rb .. rb + 7; two adjacent elements per lane
-    auto fill_tile = [&](int a, int b, int ra, int rb) {
+    // tile (a, b), a >= b, one of whose sides is the staged group: rows = matrix rows ra .. ra + 7, columns = rb .. rb + 7
+    auto fill_tile = [&](const double* sb, int base, int a, int b, int ra, int rb) {
         const int i = ra + g, k = rb + 2 * t4;
-        *reinterpret_cast<double2*>(Ts + (size_t)tri(a, b) * 64 + g * 8 + 2 * t4) = make_double2(lam(i, k), lam(i, k + 1));
+        *reinterpret_cast<double2*>(Ts + (size_t)tri(a, b) * 64 + g * 8 + 2 * t4) =
+            make_double2(lam_staged(sb, base, i, k), lam_staged(sb, base, i, k + 1));
     };
-    auto fill_rhs = [&](int slot, int base) {   // right-hand sides b and 1 of the 8 rows base .. base + 7
+    auto fill_rhs = [&](const double* sb, int slot, int base) {   // right-hand sides b and 1 of the 8 rows base .. base + 7
         if (lane < 16) {
             const int rr = lane & 7, r = lane >> 3, i = base + rr;
-            rhs[r * W + 8 * slot + rr] = i < n ? (r == 0 ? xs[i] : 1.0) : 0.0;
+            rhs[r * W + 8 * slot + rr] = i < n ? (r == 0 ? sb[8 * W1p + 8 + rr] : 1.0) : 0.0;
         }
     };
 
-    // ---- initial window: matrix rows 0 .. W - 1, group s in slot s ----
+    // ---- initial window: matrix rows 0 .. W - 1, group s in slot s; group a is staged, its tiles against the groups
+    //      b <= a are filled (every stored pair has its later group as the row side here) ----
     for (int a = 0; a < NT; a++) {
-        for (int b = 0; b <= a; b++) fill_tile(a, b, 8 * a, 8 * b);
-        fill_rhs(a, 8 * a);
+        stage_rows(8 * a);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncwarp();
+        for (int b = 0; b <= a; b++) fill_tile(stg, 8 * a, a, b, 8 * a, 8 * b);
+        fill_rhs(stg, a, 8 * a);
+        __syncwarp();
     }
-    __syncwarp();
+    stage_rows(8 * NT);   // the group entering at the end of block step 0
 
     // ---- blocked factorisation + fused forward substitutions ----
     const int passes = (W + 31) >> 5;
@@ -276,33 +331,53 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
             }
         }
         __syncwarp();
-        // (4) rank-8 trailing update on the tensor pipe: tile (a, b) -= P_a P_b' for the slots that stay
-        for (int a = 0; a < NT; a++) {
-            if (a == cs) continue;
-            const double a0 = -Ps[t4 * Wp + 8 * a + g], a1 = -Ps[(4 + t4) * Wp + 8 * a + g];
-            for (int b = 0; b <= a; b++) {
-                if (b == cs) continue;
-                const double b0 = Ps[t4 * Wp + 8 * b + g], b1 = Ps[(4 + t4) * Wp + 8 * b + g];
-                double2* cp = reinterpret_cast<double2*>(Ts + (size_t)tri(a, b) * 64 + g * 8 + 2 * t4);
-                double2 cv = *cp;
-                dgemm::dmma884(cv.x, cv.y, a0, b0);
-                dgemm::dmma884(cv.x, cv.y, a1, b1);
-                *cp = cv;
+        // (4) rank-8 trailing update on the tensor pipe: tile (a, b) -= P_a P_b' for EVERY stored pair -- the pivot
+        //     slot's panel rows are zero, so its (dead) tiles are left unchanged and the loops carry no conditions
+        if (NT_T > 0) {
+#pragma unroll
+            for (int a = 0; a < (NT_T > 0 ? NT_T : 1); a++) {
+                const double a0 = -Ps[t4 * Wp + 8 * a + g], a1 = -Ps[(4 + t4) * Wp + 8 * a + g];
+#pragma unroll
+                for (int b = 0; b <= a; b++) {
+                    const double b0 = Ps[t4 * Wp + 8 * b + g], b1 = Ps[(4 + t4) * Wp + 8 * b + g];
+                    double2* cp = reinterpret_cast<double2*>(Ts + (a * (a + 1) / 2 + b) * 64 + g * 8 + 2 * t4);
+                    double2 cv = *cp;
+                    dgemm::dmma884(cv.x, cv.y, a0, b0);
+                    dgemm::dmma884(cv.x, cv.y, a1, b1);
+                    *cp = cv;
+                }
+            }
+        } else {
+            double2* cp = reinterpret_cast<double2*>(Ts + g * 8 + 2 * t4);
+            for (int a = 0; a < NT; a++) {
+                const double a0 = -Ps[t4 * Wp + 8 * a + g], a1 = -Ps[(4 + t4) * Wp + 8 * a + g];
+                for (int b = 0; b <= a; b++, cp += 32) {
+                    const double b0 = Ps[t4 * Wp + 8 * b + g], b1 = Ps[(4 + t4) * Wp + 8 * b + g];
+                    double2 cv = *cp;
+                    dgemm::dmma884(cv.x, cv.y, a0, b0);
+                    dgemm::dmma884(cv.x, cv.y, a1, b1);
+                    *cp = cv;
+                }
             }
         }
-        // (5) the pivot slot leaves; it takes the 8 entering rows (group m + NT)
+        // (5) the pivot slot leaves; it takes the 8 entering rows (group m + NT), staged during this block step
         {
             const int rn = 8 * (m + NT);
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            __syncwarp();
+            const double* sb = stg;
             for (int a = 0; a < NT; a++) {
                 const int grp = m + (a >= cs ? a - cs : a - cs + NT);
                 const int ra = a == cs ? rn : 8 * grp;
-                if (a >= cs) fill_tile(a, cs, ra, rn);
-                else fill_tile(cs, a, rn, ra);
+                if (a >= cs) fill_tile(sb, rn, a, cs, ra, rn);
+                else fill_tile(sb, rn, cs, a, rn, ra);
             }
-            fill_rhs(cs, rn);
+            fill_rhs(sb, cs, rn);
+            __syncwarp();             // the staged group is consumed: the buffer takes the next one
+            stage_rows(rn + 8);       // lands during the next block step
         }
-        __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
     if (!ok) {
         if (lane == 0) {
             v.status[c] = 1;
@@ -318,17 +393,41 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
             dbg.out.eta_chol[(size_t)c * n * W1 + idx] = (j + e < n) ? Lc[idx] : 0.0;
         }
 
-    // ---- blocked backward: L' x = y_b + eps, L' zv = y_1, L' m = y_b ----
-    for (int e = lane; e < 3 * W; e += T) xr[e] = 0.0;
+    // ---- blocked backward: L' x = y_b + eps, L' zv = y_1, L' m = y_b (its arrays take over the window's memory) ----
     __syncwarp();
+    for (int e = lane; e < 3 * W; e += T) xr[e] = 0.0;
     {
+        // the 8 column bands of a block are one contiguous piece of the factor: staged one block ahead (cp.async), with
+        // y_b, y_1, the normals and 1 / L_jj of the block
+        auto stage_block = [&](int j0, int buf) {
+            double* dst = stgB + buf * stg_sz;
+            if (j0 >= 0) {
+                for (int idx = lane; idx < 8 * W1; idx += T) {
+                    const int bb = idx / W1, e = idx - bb * W1;
+                    const bool okk = j0 + bb < n;
+                    icarw_cp8(dst + bb * W1p + e, okk ? Lc + (size_t)(j0 + bb) * W1 + e : Lc, okk);
+                }
+                {
+                    const int which = lane >> 3, bb = lane & 7, j = j0 + bb;
+                    const double* srcv = which == 0 ? yb : (which == 1 ? y1 : (which == 2 ? zs : inv_c));
+                    icarw_cp8(dst + 8 * W1p + which * 8 + bb, j < n ? srcv + j : srcv, j < n);
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
         const int ksteps = (w + 3) >> 2;   // rows j0 + 8 .. j0 + 7 + bw below the block
-        for (int m = n8 / 8 - 1; m >= 0; m--) {
+        const int mlast = n8 / 8 - 1;
+        stage_block(8 * mlast, mlast & 1);
+        for (int m = mlast; m >= 0; m--) {
             const int j0 = 8 * m;
+            stage_block(j0 - 8, (m + 1) & 1);                 // next block; its buffer was consumed one block ago
+            asm volatile("cp.async.wait_group 1;\n" ::);     // this block's copies have landed
+            __syncwarp();
+            const double* sb = stgB + (m & 1) * stg_sz;
             // S[b][r] = sum_i L[i][j0 + b] x_r[i]:  D (8 columns b x 8 right-hand sides) += A (8 x 4: L[i][j0 + g]) B (4 x 8: x_g[i])
             double s0a = 0.0, s1a = 0.0, s0b = 0.0, s1b = 0.0;
             const int jc = j0 + g;
-            const double* lcol = Lc + (size_t)jc * W1;
+            const double* lcol = sb + g * W1p;
             for (int ks = 0; ks < ksteps; ks += 2) {
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
@@ -354,16 +453,15 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
                     const int j = j0 + b;
                     double val = 0.0;
                     if (j < n) {
-                        const double ybv = yb[j];
-                        double t = (r == 0 ? ybv + zs[j] : (r == 1 ? y1[j] : ybv)) - Ss[b * 4 + r];
+                        const double ybv = sb[8 * W1p + b];
+                        double t = (r == 0 ? ybv + sb[8 * W1p + 16 + b] : (r == 1 ? sb[8 * W1p + 8 + b] : ybv)) - Ss[b * 4 + r];
 #pragma unroll
                         for (int bb = b + 1; bb < 8; bb++)
-                            if (j0 + bb < n) t = fma(-Lc[(size_t)j * W1 + (bb - b)], xb8[bb], t);
-                        val = t * inv_c[j];
+                            if (j0 + bb < n && bb - b <= w) t = fma(-sb[b * W1p + (bb - b)], xb8[bb], t);
+                        val = t * sb[8 * W1p + 24 + b];
                     }
                     xb8[b] = val;
                 }
-                __syncwarp(0x7u);   // lane 0 has read this block's normals from zs before lane 1 overwrites them with zv
                 double* dst = r == 0 ? xs : (r == 1 ? zs : ms);
 #pragma unroll
                 for (int b = 0; b < 8; b++) {
@@ -373,6 +471,7 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
             }
             __syncwarp();
         }
+        asm volatile("cp.async.wait_group 0;\n" ::);
     }
     __threadfence_block();
     __syncwarp();

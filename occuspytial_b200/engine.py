@@ -131,10 +131,15 @@ class DeviceEngine:
         torch = self.torch
         dtype = torch.uint8 if field == _lib.F_Z else torch.float64
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            t = torch.empty((self.chains,) + self._field_shape(field), dtype=dtype, device=self.device)
-            _lib.check(self.lib.occu_get_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_get_field')
+            if chain is None:
+                t = torch.empty((self.chains,) + self._field_shape(field), dtype=dtype, device=self.device)
+                _lib.check(self.lib.occu_get_field(self.handle, field, t.data_ptr(), self.stream.cuda_stream), 'occu_get_field')
+            else:
+                t = torch.empty((1,) + self._field_shape(field), dtype=dtype, device=self.device)
+                _lib.check(self.lib.occu_get_field_chain(self.handle, field, int(chain), t.data_ptr(), self.stream.cuda_stream),
+                           'occu_get_field_chain')
             self.stream.synchronize()
-            out = (t if chain is None else t[chain:chain + 1]).cpu().numpy()
+            out = t.cpu().numpy()
         self.d2h_bytes += out.nbytes
         return out
 
