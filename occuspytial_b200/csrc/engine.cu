@@ -165,18 +165,37 @@ static int launch_gram_tc(occu_engine* e, cudaStream_t st) {
     }
     gtc::Params p;
     p.Cp = v.Cp; p.kblocks = g.kblocks; p.nsplit = g.nsplit; p.kb_per_chunk = g.kb_per_chunk; p.MT = g.MT;
-    p.n_gt = g.n_gt; p.n_ht = g.n_ht; p.Mrows = g.Mrows; p.M = v.M; p.pq = v.pq; p.ldg = v.M_pad; p.ldh = v.ldh;
-    p.scale = v.tscale; p.hshift = v.hshift; p.err = v.tc_err; p.mode = 0;
+    p.pq = v.pq; p.ldg = v.M_pad; p.ldh = v.ldh;
+    p.hshift = v.hshift; p.err = v.tc_err; p.mode = 0;
     p.order = e->tc_order;
-    p.Gpart = g.nsplit > 1 ? v.Gp : v.G;
     p.Hpart = g.nsplit > 1 ? v.Hp : v.Hpart;
-    const int nitems = g.MT * (g.n_gt + g.n_ht) * g.nsplit;
-    const int grid = nitems < e->sm_count ? nitems : e->sm_count;
-    if (e->omega_planes == gtc::SA_F32)
-        gtc::gram_tc_kernel<TC_BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA_F32>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
-    else
-        gtc::gram_tc_kernel<TC_BN, gtc::SA><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
-    e->launches++;
+    // stored planes: one launch over all column tiles.  Streamed planes (large q): groups of column tiles, each sliced
+    // into the operand buffer and consumed; the last group carries the U rows of the H tiles.
+    const int group = v.tc_group_tiles ? v.tc_group_tiles : g.n_gt;
+    for (int nt0 = 0; nt0 < g.n_gt; nt0 += group) {
+        const int ntg = g.n_gt - nt0 < group ? g.n_gt - nt0 : group;
+        const bool last = nt0 + ntg == g.n_gt;
+        p.n_gt = ntg;
+        p.n_ht = last ? g.n_ht : 0;
+        p.Mrows = v.tc_cap_rows;
+        const int col0 = nt0 * TC_BN;
+        p.M = v.M - col0 < ntg * TC_BN ? v.M - col0 : ntg * TC_BN;
+        p.scale = v.tscale + col0;
+        p.Gpart = (g.nsplit > 1 ? v.Gp : v.G) + col0;
+        if (v.tc_group_tiles) {
+            const int rows = (ntg + p.n_ht) * TC_BN;
+            gtc::slice_group_from_ut_kernel<<<rows, 256, 0, st>>>(v.UT, v.n, v.n_pad, g.Kp, v.M, g.Mg_pad, v.pq, col0, ntg * TC_BN,
+                                                                  last ? ntg * TC_BN : -1, v.tc_cap_rows, v.tscale, v.Bq);
+            e->launches++;
+        }
+        const int nitems = g.MT * (p.n_gt + p.n_ht) * g.nsplit;
+        const int grid = nitems < e->sm_count ? nitems : e->sm_count;
+        if (e->omega_planes == gtc::SA_F32)
+            gtc::gram_tc_kernel<TC_BN, gtc::SA_F32><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA_F32>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+        else
+            gtc::gram_tc_kernel<TC_BN, gtc::SA><<<grid, gtc::THREADS, gtc::Cfg<TC_BN, gtc::SA>::SMEM_BYTES, st>>>(e->tmA, e->tmB, p);
+        e->launches++;
+    }
     if (g.nsplit > 1) {
         const size_t tg = (size_t)v.Cp * v.M_pad, th = (size_t)v.Cp * v.ldh;
         gtc::reduce_parts_kernel<<<(unsigned)((tg + 255) / 256), 256, 0, st>>>(v.Gp, g.nsplit, tg, tg, v.M_pad, v.M, v.G);
@@ -434,15 +453,18 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         // slice [Z | U] once (formed on the fly from U'), encode the TMA descriptors of the two operand arrays
         e->geo = gtc::make_geometry(v.n, v.Cp, v.M, v.pq, TC_BN);
         const gtc::Geometry& g = e->geo;
-        gtc::slice_rows_from_ut_kernel<<<g.Mrows, 256, 0, st>>>(v.UT, v.n, v.n_pad, g.Kp, v.M, g.Mg_pad, v.pq, g.Mrows, v.tscale,
-                                                                 v.Bq);
+        if (v.tc_group_tiles)   // streamed planes: only the row scales are computed here
+            gtc::row_scales_from_ut_kernel<<<g.Mrows, 256, 0, st>>>(v.UT, v.n, v.n_pad, v.M, g.Mg_pad, v.pq, v.tscale);
+        else
+            gtc::slice_rows_from_ut_kernel<<<g.Mrows, 256, 0, st>>>(v.UT, v.n, v.n_pad, g.Kp, v.M, g.Mg_pad, v.pq, g.Mrows, v.tscale,
+                                                                     v.Bq);
         gtc::hshift_from_ut_kernel<<<v.ldh, 128, 0, st>>>(v.UT, v.n, v.n_pad, v.pq, v.ldh, v.hshift);
         e->launches += 2;
         FAIL_IF(cudaMemsetAsync(v.Aq, 0, (size_t)(gtc::SA + 1) * v.Cp * g.Kp, st));
         FAIL_IF(cudaMemsetAsync(v.G, 0, (size_t)v.Cp * v.M_pad * 8, st));
         FAIL_IF(cudaMemsetAsync(v.tc_err, 0, sizeof(int), st));
         const char* why = gtc::make_map(&e->tmA, v.Aq, (uint64_t)(gtc::SA + 1) * v.Cp, g.Kp, gtc::BM);
-        if (!why) why = gtc::make_map(&e->tmB, v.Bq, (uint64_t)gtc::SB * g.Mrows, g.Kp, TC_BN);
+        if (!why) why = gtc::make_map(&e->tmB, v.Bq, (uint64_t)gtc::SB * v.tc_cap_rows, g.Kp, TC_BN);
         if (!why && (cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           gtc::Cfg<TC_BN>::SMEM_BYTES) != cudaSuccess ||
                      cudaFuncSetAttribute(gtc::gram_tc_kernel<TC_BN, gtc::SA_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -77,6 +77,8 @@ struct View {
     // exact-integer Gram path on the tcgen05 tensor cores (gram_tc.cuh)
     int int8;               // 1: G and H come from the tcgen05 kind::i8 slice kernel
     int tc_Kp, tc_nsplit, tc_Mrows;
+    int tc_group_tiles;     // 0: the Z planes are stored; > 0: streamed, this many 64-column tiles per group (large q)
+    int tc_cap_rows;        // rows per plane of the B operand buffer (= tc_Mrows when stored)
     uint8_t* Aq;            // [SA + 1][Cp][tc_Kp]   base-256 digits of omega / 8, then z
     int8_t* Bq;             // [SB][tc_Mrows][tc_Kp] balanced base-256 digits of [Z | U] / column scale
     double* tscale;         // [tc_Mrows]  output scale per sliced row: 8 c_m (Gram columns), c_a (U columns)
@@ -149,7 +151,7 @@ static size_t solve_bytes_for(int q, int p, int pq) {
 }
 
 // scratch / shared-memory sizes of the tiled large-q solve (solve_logit_rsr_tiled_kernel)
-constexpr int TILED_QMAX = 1312;     // 41 tile rows: the per-chain vectors and 9 panel slots stay within shared memory
+constexpr int TILED_QMAX = 3072;     // the per-chain vectors (5 q doubles) and 9 panel slots stay within the 227 KB of shared memory
 static size_t tiled_scratch_doubles(int q, int p);
 static size_t tiled_smem_bytes(int q, int pq);
 
@@ -189,6 +191,22 @@ static int fill_dims(const occu_problem_t* P, View& v) {
         v.tc_Kp = g.Kp;
         v.tc_nsplit = g.nsplit;
         v.tc_Mrows = g.Mrows;
+        // Z planes: SB x Mrows x Kp bytes.  Kept when they fit OCCU_TC_STORE_GB (default 16 GiB: q <= ~700 at n = 10^4);
+        // beyond that they are re-formed every iteration in groups of column tiles through a buffer of OCCU_TC_GROUP_GB
+        // (default 2 GiB) -- the operand of the reference's default call at n = 10^4 (q = 1256) would be 48 GB
+        const char* sg = getenv("OCCU_TC_STORE_GB");
+        const char* gg = getenv("OCCU_TC_GROUP_GB");
+        const double store_max = (sg ? atof(sg) : 16.0) * 1073741824.0, group_max = (gg ? atof(gg) : 2.0) * 1073741824.0;
+        const double plane_bytes = (double)gtc::SB * g.Mrows * g.Kp;
+        v.tc_group_tiles = 0;
+        v.tc_cap_rows = g.Mrows;
+        if (plane_bytes > store_max) {
+            long long tiles = (long long)(group_max / ((double)gtc::SB * g.Kp * TC_BN)) - g.n_ht;
+            if (tiles < 8) tiles = 8;
+            if (tiles > g.n_gt) tiles = g.n_gt;
+            v.tc_group_tiles = (int)tiles;
+            v.tc_cap_rows = ((int)tiles + g.n_ht) * TC_BN;
+        }
     }
     if (P->model == OCCU_PROBIT_RSR) {
         // only the K-split product U'd runs.  The split depends on n alone (never on the number of chains): it fixes the
@@ -210,7 +228,7 @@ static int fill_dims(const occu_problem_t* P, View& v) {
         const bool tiled = solve_smem > 200 * 1024 || (tq && v.q >= atoi(tq));
         v.solve_stride = tiled ? (tiled_scratch_doubles(v.q, v.p) + 1) / 2 * 2 : 0;
         if (tiled ? v.q > TILED_QMAX : qb > (size_t)SOLVE_THREADS)
-            return set_err("RSR rank q too large (q <= 1312 in this build)");
+            return set_err("RSR rank q too large (q <= 3072 in this build)");
     }
     return 0;
 }
@@ -252,7 +270,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.solve_scratch = v.solve_stride ? c.take<double>(Cp * v.solve_stride) : nullptr;
     if (v.int8) {
         v.Aq = c.take<uint8_t>((size_t)(gtc::SA + 1) * Cp * v.tc_Kp);
-        v.Bq = c.take<int8_t>((size_t)gtc::SB * v.tc_Mrows * v.tc_Kp);
+        v.Bq = c.take<int8_t>((size_t)gtc::SB * v.tc_cap_rows * v.tc_Kp);
         v.tscale = c.take<double>(v.tc_Mrows);
         v.hshift = c.take<double>(v.ldh);
         v.Gp = v.tc_nsplit > 1 ? c.take<double>((size_t)v.tc_nsplit * Cp * v.M_pad) : nullptr;

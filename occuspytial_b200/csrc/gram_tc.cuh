@@ -659,6 +659,76 @@ __global__ void __launch_bounds__(256) slice_rows_from_ut_kernel(const double* _
 
 // hshift[a] = -1/2 sum_i U[i][a] from the rows of UT: one CTA per column, strided partial sums combined by a fixed
 // tree (deterministic)
+// ---- streamed Z planes (large RSR rank): the sliced operand is not kept -- at q = 1256 it is 48 GB -- but re-formed
+// every iteration, one group of column tiles at a time, into a buffer of `cap_rows` rows per plane that the Gram kernel
+// then consumes (engine.cu: launch_gram_tc).  The power-of-two row scales are computed once (row_scales_from_ut_kernel).
+// Row `local` of a group: local < z_rows -> global Gram row g_row0 + local; u_local0 <= local < u_local0 + pq -> column
+// local - u_local0 of U (last group only, u_local0 < 0 otherwise); anything else is padding (zeros).
+__global__ void __launch_bounds__(256) row_scales_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int M, int Mg_pad,
+                                                                 int pq, double* __restrict__ scale_out) {
+    __shared__ double red[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const double* ua = nullptr;
+    const double* ub = nullptr;
+    if (row < M) {
+        int a, b;
+        unvech(row, a, b);
+        ua = UT + (size_t)a * ldu;
+        ub = UT + (size_t)b * ldu;
+    } else if (row >= Mg_pad && row < Mg_pad + pq) {
+        ua = UT + (size_t)(row - Mg_pad) * ldu;
+    }
+    double mx = 0.0;
+    if (ua)
+        for (int i = tid; i < n; i += 256) mx = fmax(mx, fabs(ub ? ua[i] * ub[i] : ua[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double m8 = 0.0;
+        for (int w = 0; w < 8; w++) m8 = fmax(m8, red[w]);
+        int e = 0;
+        if (m8 > 0.0) {
+            const double f = frexp(m8, &e);
+            e += f > 0.99 ? 2 : 1;
+        }
+        const double cs = ldexp(1.0, e);
+        scale_out[row] = !ua ? 0.0 : (ub ? OMEGA_SCALE * cs : cs);
+    }
+}
+
+__global__ void __launch_bounds__(256) slice_group_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int Kp, int M,
+                                                                  int Mg_pad, int pq, int g_row0, int z_rows, int u_local0,
+                                                                  int cap_rows, const double* __restrict__ scale,
+                                                                  int8_t* __restrict__ Bq) {
+    const int local = blockIdx.x, tid = threadIdx.x;
+    const double* ua = nullptr;
+    const double* ub = nullptr;
+    double cs = 1.0;
+    if (local < z_rows && g_row0 + local < M) {
+        int a, b;
+        unvech(g_row0 + local, a, b);
+        ua = UT + (size_t)a * ldu;
+        ub = UT + (size_t)b * ldu;
+        cs = scale[g_row0 + local] * (1.0 / OMEGA_SCALE);
+    } else if (u_local0 >= 0 && local >= u_local0 && local < u_local0 + pq) {
+        ua = UT + (size_t)(local - u_local0) * ldu;
+        cs = scale[Mg_pad + local - u_local0];
+    }
+    const double mult = (double)(1LL << (8 * SB)) / cs;   // exact: cs is a power of two
+    for (int i = tid; i < Kp; i += 256) {
+        long long q = 0;
+        if (ua && i < n) q = llrint((ub ? ua[i] * ub[i] : ua[i]) * mult);
+#pragma unroll
+        for (int t = SB; t >= 1; t--) {
+            const long long d = ((q + 128) & 0xFF) - 128;
+            q = (q - d) >> 8;
+            Bq[((size_t)(t - 1) * cap_rows + local) * Kp + i] = (int8_t)d;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) hshift_from_ut_kernel(const double* __restrict__ UT, int n, int ldu, int pq, int ldh,
                                                               double* __restrict__ hshift) {
     __shared__ double part[128];

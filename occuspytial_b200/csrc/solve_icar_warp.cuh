@@ -41,16 +41,18 @@ __host__ __device__ inline int icarw_nt(int bw) {
     return need <= 8 ? (need + 1) / 2 * 2 : need;
 }
 __host__ __device__ inline int icarw_wp(int nt) { return (nt & 1) ? 8 * nt : 8 * nt + 8; }   // panel pitch = 8 mod 16 doubles
-__host__ __device__ inline int icarw_w1p(int bw) { return (bw + 1 + 1) / 2 * 2 + 2; }         // staged band row pitch (doubles)
+// staged band rows: W + 8 doubles, zero beyond the band, so that both passes read them without bounds checks (forward:
+// offsets up to W - 1; backward: up to bw + 10 <= W + 2)
+__host__ __device__ inline int icarw_pw(int nt) { return 8 * nt + 8; }
 // shared-memory layout (doubles): region A = window tiles (forward) / x ring + block sums + two staged factor blocks
 // (backward) | panel | forward residuals | one staged group of entering rows | beta system
 __host__ __device__ inline size_t icarw_region_a(int nt, int bw) {
-    const size_t tiles = (size_t)nt * (nt + 1) / 2 * 64, back = 3 * 8 * (size_t)nt + 32 + 2 * (8 * (size_t)icarw_w1p(bw) + 32);
+    const size_t tiles = (size_t)nt * (nt + 1) / 2 * 64, back = 8 * 8 * (size_t)nt + 32 + 2 * (8 * (size_t)icarw_pw(nt) + 32);
     return tiles > back ? tiles : back;
 }
 static size_t icarw_smem_bytes(int bw, int p) {
     const size_t nt = icarw_nt(bw), W = 8 * nt, Wp = icarw_wp((int)nt);
-    return (icarw_region_a((int)nt, bw) + 8 * Wp + 2 * W + (8 * (size_t)icarw_w1p(bw) + 32) + (size_t)p * p + 5 * (size_t)p) *
+    return (icarw_region_a((int)nt, bw) + 8 * Wp + 2 * W + (8 * (size_t)icarw_pw((int)nt) + 32) + (size_t)p * p + 5 * (size_t)p) *
            sizeof(double);
 }
 
@@ -75,14 +77,14 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
     const int g = lane >> 2, t4 = lane & 3;
     const int n = v.n, n4 = round_up_dev(v.n, 4), p = v.p, w = v.bw, W1 = v.bw + 1;
     const int NT = NT_T > 0 ? NT_T : icarw_nt(w), W = 8 * NT, Wp = icarw_wp(NT);
-    const int W1p = icarw_w1p(w);
+    const int W1p = icarw_pw(NT);
     const int n8 = round_up_dev(n, 8);
     const size_t Cp = v.Cp;
     const HParams* hp = v.hp;
     const int stg_sz = 8 * W1p + 32;              // 8 staged band rows + 4 x 8 scalars
     double* Ts = icw_sm;                          // [NT (NT + 1) / 2][8][8]  window tiles, pair (a, b), a >= b   (forward)
-    double* xr = icw_sm;                          // [3][W]   backward: ring of solved x, zv, m by (matrix row mod W)
-    double* Ss = xr + 3 * W;                      // [8][4]   backward: block sums
+    double* xr = icw_sm;                          // [8][W]   backward: ring of solved x, zv, m by (matrix row mod W); rows 3..7 zero
+    double* Ss = xr + 8 * W;                      // [8][4]   backward: block sums
     double* stgB = Ss + 32;                       // [2][stg_sz]  backward: staged factor blocks
     double* Ps = icw_sm + icarw_region_a(NT, w);  // [8][Wp]  panel, column-major: Ps[col][window row]
     double* rhs = Ps + 8 * Wp;                    // [2][W]   forward residuals of b and 1, by window row
@@ -171,11 +173,11 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
     //      copies land while the block step in between runs) ----
     auto stage_rows = [&](int base) {
         double* dst = stg;
-        for (int idx = lane; idx < 8 * W1; idx += T) {
-            const int rr = idx / W1, d = idx - rr * W1;
+#pragma unroll 1
+        for (int rr = 0; rr < 8; rr++) {
             const int i = base + rr;
-            const bool okk = i < n && d <= i;
-            icarw_cp8(dst + rr * W1p + d, okk ? v.Qband + (size_t)i * W1 + d : v.Qband, okk);
+            const double* srow = v.Qband + (size_t)(i < n ? i : 0) * W1;
+            for (int d = lane; d < W1; d += T) icarw_cp8(dst + rr * W1p + d, srow + d, i < n && d <= i);
         }
         if (lane < 16) {
             const int rr = lane & 7, i = base + rr;
@@ -184,19 +186,13 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    // Lambda[i][k] for a staged row i = base + rr (identity beyond n); k may lie on either side of i
+    // Lambda[hi][lo] for a staged row hi = base + rr (identity beyond n), lo <= hi within W - 1: the staged rows are zero
+    // beyond the band and for rows past n, so the read needs no bounds checks
     auto lam_staged = [&](const double* sb, int base, int i, int k) -> double {
-        // the staged rows are base .. base + 7: an element (i, k) with k > i is Lambda[k][i], available when k is staged too
-        int hi = i, lo = k;
-        if (k > i) {
-            hi = k;
-            lo = i;
-        }
-        const int d = hi - lo;
-        if (hi >= n) return d == 0 ? 1.0 : 0.0;
-        if (d > w) return 0.0;
-        double val = tau * sb[(hi - base) * W1p + d];
-        if (d == 0) val += sb[8 * W1p + (hi - base)];
+        const int hi = max(i, k), d = hi - min(i, k);
+        const int rr = hi - base;
+        double val = tau * sb[rr * W1p + d];
+        if (d == 0) val += hi < n ? sb[8 * W1p + rr] : 1.0;
         return val;
     };
     // tile (a, b), a >= b, one of whose sides is the staged group: rows = matrix rows ra .. ra + 7, columns = rb .. rb + 7
@@ -214,6 +210,8 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
 
     // ---- initial window: matrix rows 0 .. W - 1, group s in slot s; group a is staged, its tiles against the groups
     //      b <= a are filled (every stored pair has its later group as the row side here) ----
+    for (int e = lane; e < stg_sz; e += T) stg[e] = 0.0;   // the pads beyond the band stay zero for good
+    __syncwarp();
     for (int a = 0; a < NT; a++) {
         stage_rows(8 * a);
         asm volatile("cp.async.wait_group 0;\n" ::);
@@ -395,17 +393,20 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
 
     // ---- blocked backward: L' x = y_b + eps, L' zv = y_1, L' m = y_b (its arrays take over the window's memory) ----
     __syncwarp();
-    for (int e = lane; e < 3 * W; e += T) xr[e] = 0.0;
+    for (int e = lane; e < 8 * W + 32 + 2 * stg_sz; e += T) xr[e] = 0.0;   // ring, sums, staging pads
+    __syncwarp();
     {
         // the 8 column bands of a block are one contiguous piece of the factor: staged one block ahead (cp.async), with
-        // y_b, y_1, the normals and 1 / L_jj of the block
+        // y_b, y_1, the normals and 1 / L_jj of the block.  Entries of L below row n are never written: they keep the
+        // zero of the workspace, like the staged rows' pads, so nothing below needs a bounds check.
         auto stage_block = [&](int j0, int buf) {
             double* dst = stgB + buf * stg_sz;
             if (j0 >= 0) {
-                for (int idx = lane; idx < 8 * W1; idx += T) {
-                    const int bb = idx / W1, e = idx - bb * W1;
+#pragma unroll 1
+                for (int bb = 0; bb < 8; bb++) {
                     const bool okk = j0 + bb < n;
-                    icarw_cp8(dst + bb * W1p + e, okk ? Lc + (size_t)(j0 + bb) * W1 + e : Lc, okk);
+                    const double* scol = Lc + (size_t)(okk ? j0 + bb : 0) * W1;
+                    for (int e = lane; e < W1; e += T) icarw_cp8(dst + bb * W1p + e, scol + e, okk);
                 }
                 {
                     const int which = lane >> 3, bb = lane & 7, j = j0 + bb;
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
         const int ksteps = (w + 3) >> 2;   // rows j0 + 8 .. j0 + 7 + bw below the block
         const int mlast = n8 / 8 - 1;
         stage_block(8 * mlast, mlast & 1);
+        int ring0 = (8 * mlast + 8 + t4) % W;   // ring slot of row j0 + 8 + t4
         for (int m = mlast; m >= 0; m--) {
             const int j0 = 8 * m;
             stage_block(j0 - 8, (m + 1) & 1);                 // next block; its buffer was consumed one block ago
@@ -426,19 +428,17 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
             const double* sb = stgB + (m & 1) * stg_sz;
             // S[b][r] = sum_i L[i][j0 + b] x_r[i]:  D (8 columns b x 8 right-hand sides) += A (8 x 4: L[i][j0 + g]) B (4 x 8: x_g[i])
             double s0a = 0.0, s1a = 0.0, s0b = 0.0, s1b = 0.0;
-            const int jc = j0 + g;
-            const double* lcol = sb + g * W1p;
+            const double* lcol = sb + g * W1p + (8 + t4 - g);   // entry e = 8 + 4 ks + t4 - g of column j0 + g
+            const double* xg = xr + g * W;
+            int ring = ring0;
+#pragma unroll 2
             for (int ks = 0; ks < ksteps; ks += 2) {
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int i = j0 + 8 + 4 * (ks + u) + t4;
-                    const int e = i - jc;
-                    const bool okk = (ks + u) < ksteps && e <= w && i < n && jc < n;
-                    const double av = okk ? lcol[e] : 0.0;
-                    const double bv = (g < 3 && i < n) ? xr[g * W + (i % W)] : 0.0;
-                    if (u == 0) dgemm::dmma884(s0a, s1a, av, bv);
-                    else dgemm::dmma884(s0b, s1b, av, bv);
-                }
+                int ring1 = ring + 4;
+                if (ring1 >= W) ring1 -= W;
+                dgemm::dmma884(s0a, s1a, lcol[4 * ks], xg[ring]);
+                dgemm::dmma884(s0b, s1b, lcol[4 * ks + 4], xg[ring1]);   // (an odd count runs one step into the zero pad)
+                ring = ring1 + 4;
+                if (ring >= W) ring -= W;
             }
             if (t4 < 2) {   // right-hand sides 0..3 live in the lanes t4 = 0, 1
                 Ss[g * 4 + 2 * t4] = s0a + s0b;
@@ -450,25 +450,22 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
                 double xb8[8];
 #pragma unroll
                 for (int b = 7; b >= 0; b--) {
-                    const int j = j0 + b;
-                    double val = 0.0;
-                    if (j < n) {
-                        const double ybv = sb[8 * W1p + b];
-                        double t = (r == 0 ? ybv + sb[8 * W1p + 16 + b] : (r == 1 ? sb[8 * W1p + 8 + b] : ybv)) - Ss[b * 4 + r];
+                    const double ybv = sb[8 * W1p + b];
+                    double t = (r == 0 ? ybv + sb[8 * W1p + 16 + b] : (r == 1 ? sb[8 * W1p + 8 + b] : ybv)) - Ss[b * 4 + r];
 #pragma unroll
-                        for (int bb = b + 1; bb < 8; bb++)
-                            if (j0 + bb < n && bb - b <= w) t = fma(-sb[b * W1p + (bb - b)], xb8[bb], t);
-                        val = t * sb[8 * W1p + 24 + b];
-                    }
-                    xb8[b] = val;
+                    for (int bb = b + 1; bb < 8; bb++) t = fma(-sb[b * W1p + (bb - b)], xb8[bb], t);
+                    xb8[b] = t * sb[8 * W1p + 24 + b];   // 1 / L_jj, staged as zero for the padded columns j >= n
                 }
                 double* dst = r == 0 ? xs : (r == 1 ? zs : ms);
+                int slot = j0 % W;
 #pragma unroll
                 for (int b = 0; b < 8; b++) {
-                    xr[r * W + ((j0 + b) % W)] = xb8[b];
+                    xr[r * W + slot + b] = xb8[b];       // blocks are 8-aligned: no wrap inside a block
                     if (j0 + b < n) dst[j0 + b] = xb8[b];
                 }
             }
+            ring0 -= 8;
+            if (ring0 < 0) ring0 += W;
             __syncwarp();
         }
         asm volatile("cp.async.wait_group 0;\n" ::);

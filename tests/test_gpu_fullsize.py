@@ -77,10 +77,13 @@ def test_full_size_sharding_and_determinism(big):
     ((37, 57), 100, 129, 3, 3),    # n = 2109, 5253 Gram columns, 129 chains
     ((32, 40), 17, 70, 5, 2),      # other covariate counts (p = 5, r = 2): other template instances, pq = 22
     ((200, 250), 12, 3, 3, 3)])    # BASELINE config 5's site count: n = 50 000, five K chunks
-def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains, p, r):
+def test_tcgen05_gram_at_full_size_vs_numpy(shape, q, chains, p, r, monkeypatch):
     """The Omega-weighted Gram of the tcgen05 kind::i8 path (csrc/gram_tc.cuh) at sizes the small parity cases do
     not reach: every Gaussian system built from it agrees with a NumPy FP64 evaluation to 1e-10
     (reference: logit.py:226-232, 325-337, 478-485)."""
+    if q == 100:   # this case also runs with STREAMED Z planes: four groups of column tiles through a 20 MB buffer
+        monkeypatch.setenv('OCCU_TC_STORE_GB', '0.001')
+        monkeypatch.setenv('OCCU_TC_GROUP_GB', '0.02')
     from occuspytial_b200 import LogitRSRGibbs, _lib
     from occuspytial_b200.utils import make_data
     from occuspytial_b200.gibbs import _setup

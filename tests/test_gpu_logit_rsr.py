@@ -256,6 +256,43 @@ def test_large_rank_tiled_solve_vs_oracle():
     eng.close()
 
 
+def test_rank_beyond_1312_with_streamed_planes(monkeypatch):
+    """q = 1400 (beyond round 1's limit of 1312): the 985k-column joint Gram goes through STREAMED Z planes (re-formed every
+    iteration in groups of column tiles instead of stored: forced here with a 1 GiB store limit and a 0.5 GiB group buffer)
+    and the tiled solve runs with 44 tile rows.  Lambda, b, the Cholesky factor, the mean and the draw agree with the
+    oracle (reference: logit.py:325-337, 415-460, 478-485)."""
+    from occuspytial_b200 import LogitRSRGibbs, _lib
+    from occuspytial_b200.utils import make_data
+    from oracle import sweep as S
+    monkeypatch.setenv('OCCU_TC_STORE_GB', '1')
+    monkeypatch.setenv('OCCU_TC_GROUP_GB', '0.5')
+    q, chains = 1400, 2
+    Q, W, X, y, *_ = make_data(n=1600, min_v=1, max_v=4, lattice=(40, 40), random_state=5)
+    s = LogitRSRGibbs(Q, W, X, y, random_state=2, q=q)
+    f = s.fixed
+    rng = np.random.default_rng(6)
+    eng = s._make_engine(chains, seed=12, debug=True, gram_int8=True)
+    st = dict(alpha=rng.normal(size=(chains, 3)), beta=rng.normal(size=(chains, 3)), tau=rng.uniform(0.5, 2, chains),
+              eta=rng.normal(size=(chains, q)) * 0.1)
+    eng.set_start(st)
+    eng.debug_site_half()
+    z = eng.get_field(_lib.F_Z).astype(float)
+    omega = eng.get_field(_lib.F_OMEGA)
+    normals = rng.normal(size=(chains, q + 3 + 3))
+    out = eng.debug_gaussian_half(normals=normals, tau=st['tau'])
+    assert out['fails'] == 0
+    eta_new = eng.get_field(_lib.F_ETA)
+    for c in range(chains):
+        Lam, b = S.eta_rsr_system(f.K, X, omega[c], z[c] - 0.5, st['beta'][c], st['tau'][c], f.Q)
+        np.testing.assert_allclose(out['eta_prec'][c], Lam, rtol=1e-10, atol=1e-12 * np.abs(Lam).max())
+        np.testing.assert_allclose(out['eta_b'][c], b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+        eta_o, mean_o, L_o = S.gaussian_from_system(Lam, b, normals[c, :q])
+        np.testing.assert_allclose(out['eta_chol'][c], L_o, rtol=1e-9, atol=1e-11 * np.abs(L_o).max())
+        np.testing.assert_allclose(out['eta_mean'][c], mean_o, rtol=1e-8, atol=1e-10 * np.abs(mean_o).max())
+        np.testing.assert_allclose(eta_new[c], eta_o, rtol=1e-8, atol=1e-10 * np.abs(eta_o).max())
+    eng.close()
+
+
 def test_default_threshold_at_moderate_size():
     """The reference's default call LogitRSRGibbs(Q, W, X, y) (r = 0.5 -> q ~ n / 8, logit.py:409-411) beyond the
     shared-memory solve: n = 2500 gives q = 317.  Runs, keeps every chain positive definite and moves alpha."""
