@@ -139,9 +139,10 @@ int occu_sweep(occu_engine_t* eng, int n_iters, double* rec_alpha, double* rec_b
 
 /*
  * The two halves of occu_sweep: occu_sweep_enqueue only enqueues the kernels of `n_iters` iterations on `stream`
- * (no host synchronisation), occu_finish synchronises the stream and returns the number of failed chains.  Two
- * engines holding disjoint chain blocks of the same problem can be enqueued on two streams of one GPU so that one
- * block's sampling kernels (integer / FP32 pipes) overlap the other block's Gram GEMM (FP64 tensor pipe).
+ * (no host synchronisation), occu_finish synchronises the stream and returns the number of failed chains.  This is
+ * what sample() uses: every block of iterations is enqueued without waiting, the record block that has just filled
+ * crosses PCIe on a second stream meanwhile, and engines on several devices (one per GPU, driven from host threads)
+ * run concurrently.
  */
 int occu_sweep_enqueue(occu_engine_t* eng, int n_iters, double* rec_alpha, double* rec_beta, double* rec_tau,
                        int rec_start, int rec_capacity, void* stream);

@@ -220,11 +220,6 @@ static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     return 0;
 }
 
-static size_t icar_smem_bytes(const View& v) {
-    const size_t W1 = v.bw + 1;
-    return (W1 * W1 + 6 * W1 + 2 * MAX_SMALL + 8) * sizeof(double) + (size_t)v.bw * (v.bw + 1) + 16;
-}
-
 static size_t solve_smem_bytes(const View& v) { return solve_bytes_for(v.q, v.p, v.pq); }
 
 // Threads per chain in the RSR solve.  Most phases of the blocked factorisation keep only a few dozen threads busy
@@ -269,12 +264,7 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
     e->launches += 2;
     PROF_MARK(e, KC_SOLVE, st);
     if (v.model == OCCU_LOGIT_ICAR) {
-        static int use_old = -1;   // OCCU_ICAR_KERNEL=cta selects the round-1 kernels (one CTA per chain) for A/B timing
-        if (use_old < 0) {
-            const char* sel = getenv("OCCU_ICAR_KERNEL");
-            use_old = (sel && !strcmp(sel, "cta")) ? 1 : 0;
-        }
-        if (!use_old) {
+        {
             const size_t smem_w = icarw_smem_bytes(v.bw, v.p);
             size_t& configured_w = e->smem_configured[0];   // per engine: the attribute is per device
             const int nt = icarw_nt(v.bw);
@@ -297,24 +287,6 @@ static int launch_gaussian_half(occu_engine* e, const SolveDebug& dbg, double* r
             CUDA_OK(cudaGetLastError());
             return 0;
         }
-        const size_t smem_i = icar_smem_bytes(v);
-        if (v.bw > 160 || smem_i > 200 * 1024) return set_err("OCCU_ICAR_KERNEL=cta: half bandwidth too large for the round-1 kernels");
-        static size_t configured_i = 0;
-        if (smem_i > configured_i) {
-            CUDA_OK(cudaFuncSetAttribute(solve_logit_icar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
-            configured_i = smem_i;
-        }
-        const int nt = (v.bw + 4 + 7) / 8;
-        switch (nt <= 8 ? nt : 0) {
-#define CASE(NT) case NT: solve_logit_icar_mma_kernel<NT><<<v.Cp, 128, 0, st>>>(v, dbg, rb, rt, cap); break;
-            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
-#undef CASE
-            default: solve_logit_icar_kernel<<<v.Cp, ICAR_THREADS, smem_i, st>>>(v, dbg, ra, rb, rt, cap);
-        }
-        e->launches++;
-        PROF_MARK(e, KC_COUNT, st);
-        CUDA_OK(cudaGetLastError());
-        return 0;
     }
     const size_t smem = v.solve_stride ? 0 : solve_smem_bytes(v);
     size_t& configured = e->smem_configured[1];
@@ -436,6 +408,8 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     if (icar) {
         FAIL_IF(cudaMemcpyAsync((void*)v.X, P->X, (size_t)v.n * v.p * 8, cudaMemcpyDeviceToDevice, st));
         FAIL_IF(cudaMemcpyAsync((void*)v.Qband, P->Qband, (size_t)v.n * (v.bw + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        icar_nonzeros_kernel<<<(v.n + 127) / 128, 128, 0, st>>>(v.Qband, v.n, v.bw + 1, v.qnz);
+        e->launches++;
     } else {
         FAIL_IF(cudaMemcpyAsync((void*)v.Qrsr, P->Qrsr, (size_t)v.q * v.q * 8, cudaMemcpyDeviceToDevice, st));
         build_design_kernel<<<v.n, 128, v.pq * sizeof(double), st>>>(v, P->X, P->K);

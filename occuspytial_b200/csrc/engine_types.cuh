@@ -32,6 +32,7 @@ constexpr int SITE_TILE = SITE_TILE_N;
 constexpr int CHAIN_TILE = 128;  // chains per CTA in the site pass (= padding unit of the chain axis)
 constexpr int SOLVE_THREADS = 128;
 constexpr int MAX_SMALL = 32;    // max p and r
+constexpr int ICAR_NZ = 15;            // compact list of a band row's non-zero offsets (queen lattice: 4)
 constexpr int OCCU_ICAR_MAX_BW = 200;  // 26 x 27 / 2 tiles of 512 B = 180 KB of shared memory
 constexpr int TC_BN = gtc::BN_DEFAULT;  // Z columns per tile of the tcgen05 Gram (6 level accumulators side by side in TMEM)
 
@@ -93,6 +94,8 @@ struct View {
     // ICAR only
     const double* X;      // [n][p]
     const double* Qband;  // [n][bw + 1]   Qband[i][d] = Q[i][i - d]
+    uint8_t* qnz;         // [n][ICAR_NZ + 1]  count, then the offsets d >= 1 of the non-zeros of row i of the band (the
+                          //                   quadratic form eta' Q eta walks ~4 of them instead of bw); count 255: more than ICAR_NZ
     double* eta_n;        // [n_pad][Cp]   eta (= spatial effect), chain-minor
     double* Lc;           // [Cp][n][bw + 1]  column-band Cholesky factor, Lc[j][e] = L[j + e][j]
     double* scratch;      // [Cp][8][n4]   y_b, y_1, x, zv, mean, omega | 1/L_jj, kd, spare  (n4 = n rounded up to 4)
@@ -249,6 +252,7 @@ static void carve(View& v, char* base, size_t* total, int debug) {
     v.ZU = (icar || v.int8) ? nullptr : c.take<double>((size_t)v.n_pad * v.ldz);
     v.X = icar ? c.take<double>((size_t)v.n * v.p) : nullptr;
     v.Qband = icar ? c.take<double>((size_t)v.n * (v.bw + 1)) : nullptr;
+    v.qnz = icar ? c.take<uint8_t>((size_t)v.n * (ICAR_NZ + 1)) : nullptr;
     v.eta_n = icar ? c.take<double>((size_t)v.n_pad * Cp) : nullptr;
     v.Lc = icar ? c.take<double>(Cp * (size_t)v.n * (v.bw + 1)) : nullptr;
     v.scratch = icar ? c.take<double>(Cp * (size_t)8 * round_up(v.n, 4)) : nullptr;

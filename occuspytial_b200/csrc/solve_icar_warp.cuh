@@ -63,6 +63,20 @@ __device__ __forceinline__ void icarw_cp8(double* dst, const double* src, bool o
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(src), "r"(bytes));
 }
 
+// compact non-zero offsets of every band row of Q (set-up, once): qnz[i][0] = count (255: too many), then the offsets
+__global__ void icar_nonzeros_kernel(const double* __restrict__ Qband, int n, int W1, uint8_t* __restrict__ qnz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cnt = 0;
+    for (int d = 1; d < W1 && d <= i; d++) {
+        if (Qband[(size_t)i * W1 + d] != 0.0) {
+            if (cnt < ICAR_NZ) qnz[(size_t)i * (ICAR_NZ + 1) + 1 + cnt] = (uint8_t)d;
+            cnt++;
+        }
+    }
+    qnz[(size_t)i * (ICAR_NZ + 1)] = cnt <= ICAR_NZ ? (uint8_t)cnt : (uint8_t)255;
+}
+
 __device__ __forceinline__ double warp_sum(double val) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
@@ -134,8 +148,17 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
         const double ei = ms[i];
         const double* qrow = v.Qband + (size_t)i * W1;
         double sacc = 0.5 * qrow[0] * ei;
-        const int dmax = min(w, i);
-        for (int d = 1; d <= dmax; d++) sacc += qrow[d] * ms[i - d];
+        const uint8_t* nz = v.qnz + (size_t)i * (ICAR_NZ + 1);
+        const int cnt = nz[0];
+        if (cnt != 255) {   // the few non-zeros of the row (same order of summation as the dense walk: ascending offset)
+            for (int t = 1; t <= cnt; t++) {
+                const int d = nz[t];
+                sacc += qrow[d] * ms[i - d];
+            }
+        } else {
+            const int dmax = min(w, i);
+            for (int d = 1; d <= dmax; d++) sacc += qrow[d] * ms[i - d];
+        }
         part += ei * sacc;
     }
     const double quad = 2.0 * warp_sum(part);
@@ -186,20 +209,35 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    // Lambda[hi][lo] for a staged row hi = base + rr (identity beyond n), lo <= hi within W - 1: the staged rows are zero
-    // beyond the band and for rows past n, so the read needs no bounds checks
-    auto lam_staged = [&](const double* sb, int base, int i, int k) -> double {
-        const int hi = max(i, k), d = hi - min(i, k);
-        const int rr = hi - base;
-        double val = tau * sb[rr * W1p + d];
-        if (d == 0) val += hi < n ? sb[8 * W1p + rr] : 1.0;
-        return val;
-    };
-    // tile (a, b), a >= b, one of whose sides is the staged group: rows = matrix rows ra .. ra + 7, columns = rb .. rb + 7
-    auto fill_tile = [&](const double* sb, int base, int a, int b, int ra, int rb) {
+    // tile (a, b), a >= b, with the staged group (matrix rows base .. base + 7) on one side and an OLDER group on the other:
+    // rows = matrix rows ra .. ra + 7, columns = rb .. rb + 7.  Lambda[hi][lo] = tau Q[hi][hi - lo]; the staged rows are
+    // zero beyond the band and for rows past n, so the read needs no bounds checks.  Two adjacent elements per lane.
+    auto fill_tile_off = [&](const double* sb, int base, int a, int b, int ra, int rb) {
         const int i = ra + g, k = rb + 2 * t4;
-        *reinterpret_cast<double2*>(Ts + (size_t)tri(a, b) * 64 + g * 8 + 2 * t4) =
-            make_double2(lam_staged(sb, base, i, k), lam_staged(sb, base, i, k + 1));
+        double v0, v1;
+        if (ra == base) {   // rows are the staged group: hi = i
+            const double* row = sb + g * W1p + (i - k);
+            v0 = tau * row[0];
+            v1 = tau * row[-1];
+        } else {            // columns are the staged group: hi = k
+            const double* row = sb + (k - base) * W1p + (k - i);
+            v0 = tau * row[0];
+            v1 = tau * row[W1p + 1];
+        }
+        *reinterpret_cast<double2*>(Ts + (size_t)tri(a, b) * 64 + g * 8 + 2 * t4) = make_double2(v0, v1);
+    };
+    // the diagonal tile of the staged group (symmetric; identity beyond n)
+    auto fill_tile_diag = [&](const double* sb, int base, int a) {
+        double vv[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int ri = g, ci = 2 * t4 + u;
+            const int hi = max(ri, ci), d = hi - min(ri, ci);
+            double val = tau * sb[hi * W1p + d];
+            if (d == 0) val += base + hi < n ? sb[8 * W1p + hi] : 1.0;
+            vv[u] = val;
+        }
+        *reinterpret_cast<double2*>(Ts + (size_t)tri(a, a) * 64 + g * 8 + 2 * t4) = make_double2(vv[0], vv[1]);
     };
     auto fill_rhs = [&](const double* sb, int slot, int base) {   // right-hand sides b and 1 of the 8 rows base .. base + 7
         if (lane < 16) {
@@ -216,7 +254,8 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
         stage_rows(8 * a);
         asm volatile("cp.async.wait_group 0;\n" ::);
         __syncwarp();
-        for (int b = 0; b <= a; b++) fill_tile(stg, 8 * a, a, b, 8 * a, 8 * b);
+        for (int b = 0; b < a; b++) fill_tile_off(stg, 8 * a, a, b, 8 * a, 8 * b);
+        fill_tile_diag(stg, 8 * a, a);
         fill_rhs(stg, a, 8 * a);
         __syncwarp();
     }
@@ -365,10 +404,13 @@ __global__ void __launch_bounds__(ICARW_THREADS) solve_logit_icar_warp_kernel(co
             __syncwarp();
             const double* sb = stg;
             for (int a = 0; a < NT; a++) {
-                const int grp = m + (a >= cs ? a - cs : a - cs + NT);
-                const int ra = a == cs ? rn : 8 * grp;
-                if (a >= cs) fill_tile(sb, rn, a, cs, ra, rn);
-                else fill_tile(sb, rn, cs, a, rn, ra);
+                if (a == cs) {
+                    fill_tile_diag(sb, rn, cs);
+                } else {
+                    const int grp = m + (a >= cs ? a - cs : a - cs + NT);
+                    if (a > cs) fill_tile_off(sb, rn, a, cs, 8 * grp, rn);
+                    else fill_tile_off(sb, rn, cs, a, rn, 8 * grp);
+                }
             }
             fill_rhs(sb, cs, rn);
             __syncwarp();             // the staged group is consumed: the buffer takes the next one

@@ -207,6 +207,13 @@ class GibbsBase:
         """Everything the device engine needs, as host arrays (see include/occu_b200.h: occu_problem_t)."""
         f = self.fixed
         n = f.n
+        r = self.W[self.W.surveyed[0]].shape[1]
+        if self.X.shape[1] > 32 or r > 8:
+            raise ValueError('the engine supports at most 32 occupancy covariates (columns of X) and 8 detection '
+                             f'covariates (columns of W); got {self.X.shape[1]} and {r}')
+        q = getattr(f, 'q', None)
+        if q is not None and q > 3072:
+            raise ValueError(f'RSR rank q = {q} exceeds the engine limit of 3072; pass a smaller q or a larger threshold r')
         W_rows, visit_ptr = self.W.to_csr(n)
         y_rows, y_ptr = self.y.to_csr(n, dtype=np.uint8)
         _check_visits_match(visit_ptr, y_ptr)

@@ -16,9 +16,16 @@ class LogitICARGibbs(GibbsBase):
     Lambda = tau Q + diag(omega_b), conditioned on 1'eta = 0.  The reference perturbs b with 2n - 1
     normals through a dense eigen-factor of Q and solves with MINRES at rtol 1e-5 (logit.py:73-99);
     the engine factorises Lambda exactly with a fixed-pattern banded Cholesky per chain.
+
+    Limits of the engine (checked before an engine is created, ``ValueError``): the sites are reordered by reverse
+    Cuthill-McKee and the half bandwidth of the reordered Q must not exceed 200 -- the sliding window of the
+    factorisation lives in shared memory.  A queen lattice with sides a <= b has half bandwidth about a + 1, so lattices
+    up to ~198 sites on the short side fit; the reference's MINRES path has no such limit (but costs O(n) dense memory for
+    its eigen-factor).  At most 32 occupancy covariates and 8 detection covariates.
     """
 
     _model = 'logit_icar'
+    MAX_HALF_BANDWIDTH = 200
 
     def __init__(self, Q, W, X, y, hparams=None, random_state=None):
         super().__init__(Q, W, X, y, hparams, random_state)
@@ -55,6 +62,9 @@ class LogitICARGibbs(GibbsBase):
     def _problem_arrays(self):
         from ..data import Data
         perm, bw = self._band()
+        if bw > self.MAX_HALF_BANDWIDTH:
+            raise ValueError(f'half bandwidth {bw} of the reordered spatial precision matrix exceeds the engine limit of '
+                             f'{self.MAX_HALF_BANDWIDTH} (LogitICARGibbs keeps the factorisation window in shared memory)')
         f = self.fixed
         n = f.n
         inv = self._inv

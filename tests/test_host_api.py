@@ -228,3 +228,29 @@ def test_abi_library_exports_every_declared_symbol():
     P.abi_version, P.model, P.n, P.p, P.r, P.q, P.V, P.chains = _lib.ABI_VERSION, 0, 1000, 3, 3, 64, 2500, 4096
     nbytes = _lib.load().occu_workspace_bytes(ctypes.byref(P))
     assert 2e8 < nbytes < 2e9
+
+
+def test_engine_limits_and_input_checks_raise_before_any_device_work():
+    """Limits of the engine surface as ValueError on the host (no GPU needed): ICAR half bandwidth, covariate counts, RSR
+    rank; W and y must describe the same visits (the reference fails with a shape error in W.T @ y, logit.py:223)."""
+    from occuspytial_b200 import LogitICARGibbs
+    from occuspytial_b200.gibbs.base import _check_visits_match
+    from occuspytial_b200.utils import make_data
+    Q, W, X, y, *_ = make_data(n=150, min_v=1, max_v=4, lattice=(10, 15), random_state=1)
+    s = LogitICARGibbs(Q, W, X, y, random_state=1)
+    perm, bw = s._band()
+    assert 10 <= bw <= 17
+    prob = s._problem_arrays()
+    assert prob['icar_bw'] == bw and prob['Qband'].shape == (150, bw + 1)
+    s.MAX_HALF_BANDWIDTH = bw - 1
+    with pytest.raises(ValueError, match='half bandwidth'):
+        s._problem_arrays()
+    y_bad = dict(y)
+    site = next(iter(y_bad))
+    y_bad[site] = np.concatenate([y_bad[site], [0]])
+    s2 = LogitICARGibbs(Q, W, X, y_bad, random_state=1)
+    with pytest.raises(ValueError, match='same number of visits per site'):
+        s2._problem_arrays()
+    _check_visits_match(np.array([0, 2, 5]), np.array([0, 2, 5]))
+    with pytest.raises(ValueError, match='first mismatch at site 1'):
+        _check_visits_match(np.array([0, 2, 5]), np.array([0, 2, 4]))
