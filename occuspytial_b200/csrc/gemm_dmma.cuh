@@ -177,11 +177,15 @@ __global__ void GEMM_BOUNDS gemm_tn_kernel(const Args g) {
 }
 
 inline cudaError_t launch(const Args& a, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    // the attribute belongs to the DEVICE: one flag per device (a process may drive an engine on every GPU of the box)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     int items = (a.M / BM) * (a.N / BN);
     if (a.A2 && a.ksplit > 0) items += (a.M / BM) * (a.N2 / BN) * a.ksplit;

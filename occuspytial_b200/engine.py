@@ -12,6 +12,19 @@ from . import _lib
 
 _MODEL_IDS = {'logit_rsr': _lib.LOGIT_RSR, 'probit_rsr': _lib.PROBIT_RSR, 'logit_icar': _lib.LOGIT_ICAR}
 
+# one pinned staging buffer per device and concurrent engine slot, kept for the life of the process: page-locking memory is a slow driver call
+# (tens of milliseconds when several processes do it at once), not something to repeat in every sample() call
+_PINNED = {}
+
+
+def _pinned_buffer(torch, device, slot, count):
+    key = (str(device), slot)   # engines that run at the same time (one per host thread) use different slots
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < count:
+        buf = torch.empty(max(count, 1 << 16), dtype=torch.float64, pin_memory=True)
+        _PINNED[key] = buf
+    return buf[:count]
+
 
 def _torch():
     import torch
@@ -35,7 +48,7 @@ class DeviceEngine:
     """
 
     def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False,
-                 gram_int8=False, workspace=None):
+                 gram_int8=False, workspace=None, slot=0):
         import time as _time
         t_begin = _time.perf_counter()
         torch = _torch()
@@ -46,6 +59,7 @@ class DeviceEngine:
         self.chains = int(chains)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.slot = int(slot)
         X = np.ascontiguousarray(problem['X'], dtype=np.float64)
         self.n, self.p = X.shape
         W_rows = np.ascontiguousarray(problem['W_rows'], dtype=np.float64)
@@ -158,8 +172,11 @@ class DeviceEngine:
             parts.append(arr)
             offsets.append(off)
             off += arr.size
+        import time as _time
+        t0 = _time.perf_counter()
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            host = torch.empty(off, dtype=torch.float64, pin_memory=True)
+            host = _pinned_buffer(torch, self.device, self.slot, off)
+            t1 = _time.perf_counter()
             hv = host.numpy()
             for arr, o in zip(parts, offsets):
                 hv[o:o + arr.size] = arr.reshape(-1)
@@ -169,7 +186,9 @@ class DeviceEngine:
             for (field, _), o in zip(fields, offsets):
                 _lib.check(self.lib.occu_set_field(self.handle, field, dev.data_ptr() + 8 * o, self.stream.cuda_stream),
                            'occu_set_field')
-            self.stream.synchronize()
+            t2 = _time.perf_counter()
+            self.stream.synchronize()   # the staging buffer is free again after this
+        self.setup_seconds.update(start_pin=t1 - t0, start_enqueue=t2 - t1, start_sync=_time.perf_counter() - t2)
 
     # ---- sampling ------------------------------------------------------------------------------
     def alloc_record(self, capacity):

@@ -221,7 +221,7 @@ class GibbsBase:
                     site_class=f.site_class, tau_rate=f.tau_rate, tau_shape=f.tau_shape,
                     a_mu=f.a_mu, a_prec=f.a_prec, b_mu=f.b_mu, b_prec=f.b_prec)
 
-    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=None):
+    def _make_engine(self, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False, gram_int8=None, slot=0):
         """Engine for ``chains`` chains.  ``gram_int8``: True / False force the Gram path of LogitRSR (exact integer
         slicing on the tcgen05 tensor cores / hand-written FP64 DMMA kernel); None picks the tcgen05 path when the
         problem is large enough for it to pay (>= 1024 sites; the rule must not depend on the number of chains, or a
@@ -244,12 +244,12 @@ class GibbsBase:
         ws = self.__dict__.get('_ws_cache', {}).pop(key, None)   # the previous run's workspace on this device, if any
         try:
             return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
-                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8, workspace=ws)
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=gram_int8, workspace=ws, slot=slot)
         except EngineError as exc:
             if not (auto and gram_int8 and 'INT8' in str(exc)):
                 raise
             return DeviceEngine(self._model, problem, chains, seed, chain_offset=chain_offset,
-                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=False, workspace=ws)
+                                device=device, debug=debug, pg_fp64=pg_fp64, gram_int8=False, workspace=ws, slot=slot)
 
     def step(self):
         """Step through one iteration of the sampler.
@@ -299,7 +299,7 @@ class GibbsBase:
             return [None]
         return [torch.device('cuda', i) for i in range(use)]
 
-    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries):
+    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries, slot=0):
         """Chains [lo, hi) in lock-step on one device.  Returns (host arrays, summary blocks or None, stats)."""
         import time as _time
         import torch
@@ -307,7 +307,7 @@ class GibbsBase:
         t_begin = _time.perf_counter()
         arrays = self._start_arrays_range(seed, lo, hi, start)
         t_start = _time.perf_counter()
-        engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8)
+        engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8, slot=slot)
         summaries = None
         try:
             engine.set_start(self._start_to_engine(arrays))
@@ -438,7 +438,7 @@ class GibbsBase:
             def job(k):
                 dev, a, b = jobs[k]
                 return self._run_shard(dev, a, b, seed, start, size, burnin, bar if k == 0 else None, pg_fp64, gram_int8,
-                                       want_summaries=True)
+                                       want_summaries=True, slot=k)
             if len(jobs) == 1:
                 results = [job(0)]
             else:
