@@ -477,11 +477,24 @@ class GibbsBase:
         if draws < 4:
             return None
         have = bool(results) and all(r[1] is not None for r in results)
+        import torch
+        names = list(dims)
+        widths = [dims[k] for k in names]
+
+        def split(packed):   # (chains, sum(dims), W) -> {name: (chains, dim, W)}
+            out, o = {}, 0
+            for k, d in zip(names, widths):
+                out[k] = packed[:, o:o + d]
+                o += d
+            return out
+
+        def pack(result):    # one tensor per engine: a single copy / a single collective moves all three parameters
+            return torch.cat([result[1][k] for k in names], dim=1)
+
         if world == 1:
             if not have:
                 return None
-            return {k: np.concatenate([r[1][k].cpu().numpy() for r in results], axis=0) for k in dims}
-        import torch
+            return split(np.concatenate([pack(r).cpu().numpy() for r in results], axis=0))
         import torch.distributed as dist
         from .parallel import allgather_summaries
         # every rank must agree on whether the collective runs (a rank that flushed in blocks has no device summaries)
@@ -492,14 +505,11 @@ class GibbsBase:
         if int(flag.item()) == 0:
             return None
         W = 6 + _summary_lag(draws) + 1
-        out = {}
-        for k, d in dims.items():
-            if have:
-                t = torch.cat([r[1][k] for r in results], dim=0)
-            else:
-                t = torch.zeros((0, d, W), dtype=torch.float64, device=dev)
-            out[k] = allgather_summaries(t, chains).cpu().numpy()
-        return out
+        if have:
+            t = torch.cat([pack(r) for r in results], dim=0)
+        else:
+            t = torch.zeros((0, sum(widths), W), dtype=torch.float64, device=dev)
+        return split(allgather_summaries(t, chains).cpu().numpy())
 
     def _run(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0):
         """Single-chain entry point kept for API compatibility (base.py:214-241)."""
