@@ -262,9 +262,8 @@ def run_b200(args):
     if rank == 0:
         clocks.start()          # before the warm-up, so that short timed regions still collect samples
     seed = 12345
-    start = sampler._start_arrays_range(seed, lo, hi, None)
     eng = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
-    eng.set_start(start)
+    eng.draw_start(seed, *sampler._DEFAULT_START)
     rec = eng.alloc_record(args.steps)
     fails = eng.sweep(args.warmup)
     launches0 = eng.launches
@@ -300,7 +299,7 @@ def run_b200(args):
     fp64_info, dmma_info = None, None
     if rank == 0 and not args.pg_fp64:
         e2 = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=True, gram_int8=GRAM[args.gram])
-        e2.set_start(start)
+        e2.draw_start(seed, *sampler._DEFAULT_START)
         e2.sweep(3)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(e2.stream):
@@ -315,7 +314,7 @@ def run_b200(args):
         del e2
     if gram_path == 'int8' and rank == 0:
         e2 = sampler._make_engine(local, seed, chain_offset=lo, device=dev, pg_fp64=args.pg_fp64, gram_int8=False)
-        e2.set_start(start)
+        e2.draw_start(seed, *sampler._DEFAULT_START)
         e2.sweep(5)
         e2.set_profiling(True)
         e2.sweep(8)
@@ -334,7 +333,7 @@ def run_b200(args):
         kw = dict(chains=chains_total, progressbar=False, pg_fp64=args.pg_fp64, gram_int8=GRAM[args.gram])
         if world == 1:
             kw['device'] = dev      # one GPU, as --gpus says (a plain call would fan out over every visible GPU)
-        sampler.sample(max(8, args.warmup // 5), burnin=2, **kw)
+        sampler.sample(args.steps + args.warmup, burnin=args.warmup, **kw)   # same shape as the timed calls: sizes the staging buffers
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -366,8 +365,8 @@ def run_b200(args):
                'r_hat_tau_from_device_summaries': float(post.summary.loc['tau', 'r_hat']),
                'note': f'median of three timed sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) calls (all three '
                        'listed in timed_calls_s), wall clock incl. problem upload, start values, all iterations, per-chain '
-                       'summary blocks (all-gathered over the ranks) and the copy of the recorded draws to host; one short '
-                       'untimed call of the same API before them'}
+                       'summary blocks (all-gathered over the ranks) and the copy of the recorded draws to host; one '
+                       'untimed call of the same API and size before them'}
 
     if rank != 0:
         if world > 1:

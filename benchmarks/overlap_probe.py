@@ -1,30 +1,52 @@
-import sys, time, json
-sys.path.insert(0, '/root/repo')
-import numpy as np, torch
-from occuspytial_b200 import LogitRSRGibbs
-from occuspytial_b200.utils import make_data
-from occuspytial_b200.gibbs import _setup
-Q, W, X, y, *_ = make_data(n=10000, min_v=2, max_v=8, lattice=(100, 100), random_state=0)
-K = _setup.rsr_basis(Q, X, q=64)
-s = LogitRSRGibbs(Q, W, X, y, random_state=10, K=K)
-C = 4096
-for splits in (1, 2, 4):
-    per = C // splits
-    start = s._start_arrays(C, None)
-    engs = []
-    for k in range(splits):
-        e = s._make_engine(per, 123, chain_offset=k * per)
-        e.set_start({kk: v[k * per:(k + 1) * per] for kk, v in start.items()})
-        engs.append(e)
-    for e in engs: e.sweep_enqueue(30)
-    for e in engs: e.finish()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    steps = 60
-    for e in engs: e.sweep_enqueue(steps)
-    for e in engs: e.finish()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(json.dumps({'splits': splits, 'ms_per_step': 1e3 * dt / steps, 'chain_it_per_s': C * steps / dt}), flush=True)
-    for e in engs: e.close()
-    torch.cuda.empty_cache()
+"""Do the ALU-bound site pass and the tensor-bound Gram overlap when the chains are split over several engines on
+separate streams of ONE device?  Aggregate ms per iteration of E engines x (4096 / E) chains (headline workload).
+
+  python benchmarks/overlap_probe.py [engines ...]      env: OCCU_B200_LIB (library variant), OCCU_GRAM_PRIO
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, __file__.rsplit('/', 2)[0])
+import bench   # noqa: E402
+
+
+def main():
+    counts = [int(a) for a in sys.argv[1:]] or [1, 2, 4]
+    sys.argv = sys.argv[:1]
+    from occuspytial_b200 import LogitRSRGibbs
+    wl = bench.workload(bench.parse())
+    sampler = LogitRSRGibbs(wl['Q'], wl['W'], wl['X'], wl['y'], random_state=10, K=wl['K'])
+    total, warm, iters, chunk = 4096, 20, 60, 5
+    for E in counts:
+        per = total // E
+        engines = []
+        for k in range(E):
+            eng = sampler._make_engine(per, 12345, chain_offset=k * per, device='cuda:0', slot=k)
+            eng.set_start(sampler._start_arrays_range(12345, k * per, (k + 1) * per, None))
+            engines.append(eng)
+
+        def run(n):
+            for _ in range(n // chunk):
+                for eng in engines:
+                    eng.sweep_enqueue(chunk)
+            return sum(eng.finish() for eng in engines)
+        run(warm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fails = run(iters)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({'lib': os.path.basename(os.environ.get('OCCU_B200_LIB', 'default')),
+                          'gram_prio': os.environ.get('OCCU_GRAM_PRIO', '0'), 'engines': E, 'chains_per_engine': per,
+                          'ms_per_iteration': 1e3 * dt / iters, 'chain_its_per_s': total * iters / dt, 'fails': fails}),
+              flush=True)
+        for eng in engines:
+            eng.close()
+
+
+if __name__ == '__main__':
+    main()

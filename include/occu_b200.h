@@ -128,6 +128,17 @@ int occu_get_field_chain(occu_engine_t* eng, int field, int chain, void* dst, vo
 int occu_reset(occu_engine_t* eng, void* stream);
 
 /*
+ * Default start values of every chain, drawn on the device (GibbsBase._initialize_default_start, base.py:199-211, with the
+ * overrides of logit.py:462-466 and probit.py:155-160), followed by occu_reset:
+ *   tau ~ Gamma(1/2, scale 1 / tau_rate); alpha ~ N(a_mu, 100 a_prec); beta ~ N(b_mu, 100 b_prec) (Cholesky method);
+ *   eta ~ eta_scale * N(0, I) (RSR samplers: 5), minus its mean over the sites when centre_eta != 0 (ICAR sampler);
+ *   probit: eps ~ N(0, I_n).
+ * The draws are Philox blocks addressed by (seed; global chain id, element, field): a chain's start does not depend on
+ * how the job is sharded.  Fails if 100 a_prec or 100 b_prec is not positive definite.
+ */
+int occu_draw_start(occu_engine_t* eng, uint64_t seed, double eta_scale, int centre_eta, void* stream);
+
+/*
  * Advance all chains by `n_iters` full Gibbs iterations (the loop of GibbsBase._run, base.py:236-239,
  * with <Sampler>.step() = logit.py:254-266 / probit.py:262-270 as the body).  When `rec_alpha` is not
  * NULL, iteration j of this call is stored at draw index rec_start + j (Chain.append, chain.py:56-74):

@@ -47,6 +47,7 @@ SIGNATURES = {
     'occu_get_field': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_get_field_chain': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'occu_reset': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'occu_draw_start': (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p]),
     'occu_sweep': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'occu_sweep_enqueue': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'occu_finish': (C.c_int, [C.c_void_p, C.c_void_p]),

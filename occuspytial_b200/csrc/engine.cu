@@ -317,6 +317,22 @@ __global__ void gather_chain_kernel(const T* __restrict__ src, T* __restrict__ d
     if (e < d) dst[e] = src[(size_t)e * Cp + chain];
 }
 
+// lower Cholesky factor of scale * A (d x d, row-major) on the host; false if the matrix is not positive definite
+static bool host_cholesky_scaled(const double* A, int d, double scale, double* L) {
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = scale * A[i * d + j];
+            for (int k = 0; k < j; k++) s -= L[i * d + k] * L[j * d + k];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[i * d + i] = sqrt(s);
+            } else {
+                L[i * d + j] = s / L[j * d + j];
+            }
+        }
+    return true;
+}
+
 extern "C" {
 
 const char* occu_last_error(void) { return g_err; }
@@ -358,6 +374,7 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
     e->ws = (char*)workspace;
     e->ws_bytes = need;
     e->profiling = 0;
+    e->start_ok = false;
     {
         int dev = 0;
         e->sm_count = 148;
@@ -390,6 +407,10 @@ int occu_create(const occu_problem_t* P, void* workspace, size_t workspace_bytes
         }
         h.b_pm[a] = s;
     }
+    for (int a = 0; a < v.r; a++) h.a_mu[a] = P->a_mu[a];
+    for (int a = 0; a < v.p; a++) h.b_mu[a] = P->b_mu[a];
+    h.start_ok = host_cholesky_scaled(P->a_prec, v.r, 100.0, h.a_chol) && host_cholesky_scaled(P->b_prec, v.p, 100.0, h.b_chol);
+    e->start_ok = h.start_ok != 0;
 #define FAIL_IF(call)                                                        \
     do {                                                                     \
         cudaError_t _e = (call);                                             \
@@ -617,6 +638,31 @@ int occu_reset(occu_engine_t* e, void* stream) {
     e->omega_in_slices = false;
     CUDA_OK(cudaMemsetAsync(v.status, 0, (size_t)v.Cp * 4, st));
     e->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int occu_draw_start(occu_engine_t* e, uint64_t seed, double eta_scale, int centre_eta, void* stream) {
+    if (!e) return set_err("null engine");
+    if (!e->start_ok) return set_err("100 * a_prec or 100 * b_prec is not positive definite: no default start values");
+    if (occu_reset(e, stream)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const View& v = e->v;
+    void* eta; int d, u8;
+    if (field_info(e, OCCU_F_ETA, &eta, &d, &u8)) return -1;
+    draw_start_small_kernel<<<(v.Cp + 127) / 128, 128, 0, st>>>(v, seed);
+    const size_t total = (size_t)d * v.Cp;
+    draw_start_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v, seed, (double*)eta, d, eta_scale, START_ETA);
+    e->launches += 2;
+    if (centre_eta) {
+        centre_rows_kernel<<<(v.Cp + 31) / 32, dim3(32, 8), 0, st>>>((double*)eta, d, v.Cp);
+        e->launches++;
+    }
+    if (v.eps) {
+        const size_t tot = (size_t)v.n * v.Cp;
+        draw_start_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(v, seed, v.eps, v.n, 1.0, START_EPS);
+        e->launches++;
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -47,6 +47,11 @@ struct HParams {
     double tau_rate, tau_shape;
     double a_prec[MAX_SMALL * MAX_SMALL], b_prec[MAX_SMALL * MAX_SMALL];
     double a_pm[MAX_SMALL], b_pm[MAX_SMALL];  // prec @ mu
+    // default start values (occu_draw_start): prior means and the lower Cholesky factors of 100 a_prec / 100 b_prec
+    // (base.py:199-211 draws alpha, beta ~ N(mu, 100 prec): the precision used as a covariance), row-major
+    double a_mu[MAX_SMALL], b_mu[MAX_SMALL];
+    double a_chol[MAX_SMALL * MAX_SMALL], b_chol[MAX_SMALL * MAX_SMALL];
+    int start_ok;   // both factorisations succeeded
 };
 
 // device view of an engine (passed to kernels by value)
@@ -124,6 +129,7 @@ struct occu_engine {
     bool low_planes_dirty;  // planes SA_F32 .. SA - 1 hold digits of an older 48-bit omega
     bool omega_in_slices;   // ... and v.omega was NOT written by the last site pass (non-debug engines; probit: omega_b = d + eps)
     int profiling;
+    bool start_ok;          // the Cholesky factors of the default start values exist (HParams::a_chol / b_chol)
     double kernel_ms[KC_COUNT];
     long long kernel_calls[KC_COUNT];
     cudaEvent_t ev[KC_COUNT + 1];

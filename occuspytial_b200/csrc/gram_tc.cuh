@@ -55,6 +55,9 @@ constexpr int NLEV = LMAX - 1;    // levels 2 .. LMAX
 constexpr int BM = 128;           // chains per tile (TMEM lanes)
 constexpr int BK = 64;            // bytes (= int8 elements) of K per stage, one SWIZZLE_64B row
 constexpr int BN_DEFAULT = SB == 6 ? 64 : 80;  // Z columns per tile: NLEV x BN TMEM columns, 3 stages within 227 KB
+#ifndef GTC_MAX_STAGES
+#define GTC_MAX_STAGES 4
+#endif
 #ifndef GTC_STAGES
 #define GTC_STAGES 3
 #endif
@@ -85,7 +88,7 @@ struct Cfg {
     static constexpr int EXTRA = 1024 /* alignment slack */ + 256 /* barriers */;
     // as many stages as fit the 227 KB a CTA can own, at least STAGES_MIN, at most 4
     static constexpr int FIT = (227 * 1024 - EXTRA) / STAGE_BYTES;
-    static constexpr int STAGES = FIT < STAGES_MIN ? STAGES_MIN : (FIT > 4 ? 4 : FIT);
+    static constexpr int STAGES = FIT < STAGES_MIN ? STAGES_MIN : (FIT > GTC_MAX_STAGES ? GTC_MAX_STAGES : FIT);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA;
     static_assert(SMEM_BYTES <= 227 * 1024, "stages must fit the 227 KB of shared memory a CTA can own");
 };

@@ -37,6 +37,66 @@ __global__ void reset_z_kernel(View v) {
     if (v.kd) v.kd[idx] = (double)zc - 0.5;
 }
 
+// ------------------------------------------------------------------------------------------------
+// default start values, drawn on the device (base.py:199-211, logit.py:462-466, probit.py:155-160): a chain's values are
+// addressed by (seed; global chain id, element, START_ITER, field) only -- independent of how the chains are sharded
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t START_ITER = 0xFFFFFFFFu;   // Philox iteration coordinate no sweep reaches
+enum { START_TAU = 0, START_ALPHA = 1, START_BETA = 2, START_ETA = 3, START_EPS = 4 };
+
+// dst [d][Cp] <- scale * N(0, 1); padded chains replicate chain (c mod C) like to_chain_minor_kernel
+__global__ void draw_start_rows_kernel(View v, uint64_t seed, double* __restrict__ dst, int d, double scale, uint32_t field) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)d * v.Cp) return;
+    const uint32_t e = (uint32_t)(idx / v.Cp), c = (uint32_t)(idx % v.Cp);
+    Philox g;
+    g.init(seed, (uint32_t)v.chain_offset + c % (uint32_t)v.C, e, START_ITER, field);
+    dst[idx] = scale * g.normal_d();
+}
+
+// x [d][Cp] <- x - mean over the d rows, per chain (base.py:202-203); block (32, 8), one CTA per 32 chains
+__global__ void centre_rows_kernel(double* __restrict__ x, int d, int Cp) {
+    __shared__ double part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (c < Cp)
+        for (int e = threadIdx.y; e < d; e += 8) s += x[(size_t)e * Cp + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    double m = 0.0;
+    for (int k = 0; k < 8; k++) m += part[k][threadIdx.x];
+    m /= (double)d;
+    if (c < Cp)
+        for (int e = threadIdx.y; e < d; e += 8) x[(size_t)e * Cp + c] -= m;
+}
+
+// tau ~ Gamma(1/2, scale 1 / tau_rate) = N(0,1)^2 / (2 tau_rate); alpha = a_mu + L_a z; beta = b_mu + L_b z.  One thread per chain.
+__global__ void draw_start_small_kernel(View v, uint64_t seed) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.Cp) return;
+    const uint32_t gid = (uint32_t)v.chain_offset + (uint32_t)(c % v.C);
+    const HParams* hp = v.hp;
+    Philox g;
+    g.init(seed, gid, 0u, START_ITER, START_TAU);
+    const double zt = g.normal_d();
+    v.tau[c] = 0.5 * zt * zt / hp->tau_rate;
+    double z[MAX_SMALL];
+    g.init(seed, gid, 0u, START_ITER, START_ALPHA);
+    for (int j = 0; j < v.r; j++) z[j] = g.normal_d();
+    for (int a = 0; a < v.r; a++) {
+        double s = hp->a_mu[a];
+        for (int b = 0; b <= a; b++) s += hp->a_chol[a * v.r + b] * z[b];
+        v.alpha[(size_t)a * v.Cp + c] = s;
+    }
+    g.init(seed, gid, 0u, START_ITER, START_BETA);
+    for (int j = 0; j < v.p; j++) z[j] = g.normal_d();
+    for (int a = 0; a < v.p; a++) {
+        double s = hp->b_mu[a];
+        for (int b = 0; b <= a; b++) s += hp->b_chol[a * v.p + b] * z[b];
+        v.theta[(size_t)a * v.Cp + c] = s;
+    }
+}
+
 __global__ void set_control_kernel(Control* c, uint32_t iter, int first, int rec_index, int clear_fails) {
     c->iter = iter;
     c->first = first;

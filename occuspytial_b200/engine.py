@@ -17,13 +17,32 @@ _MODEL_IDS = {'logit_rsr': _lib.LOGIT_RSR, 'probit_rsr': _lib.PROBIT_RSR, 'logit
 _PINNED = {}
 
 
-def _pinned_buffer(torch, device, slot, count):
-    key = (str(device), slot)   # engines that run at the same time (one per host thread) use different slots
+def _pinned_buffer(torch, device, slot, count, kind='h2d'):
+    """``count`` float64 elements of page-locked host memory, cached per (device, slot, direction)."""
+    key = (str(device), slot, kind)   # engines that run at the same time (one per host thread) use different slots
     buf = _PINNED.get(key)
     if buf is None or buf.numel() < count:
-        buf = torch.empty(max(count, 1 << 16), dtype=torch.float64, pin_memory=True)
+        grow = 0 if buf is None else 2 * buf.numel()
+        buf = torch.empty(max(count, grow, 1 << 16), dtype=torch.float64, pin_memory=True)
         _PINNED[key] = buf
     return buf[:count]
+
+
+_D2H_STAGING_MAX = 1 << 29   # results above 512 MiB take the plain pageable copy instead of a page-locked staging buffer
+
+
+# ... and one CUDA stream per device and slot: torch's caching allocator keeps freed blocks per stream, so an engine that runs on
+# the stream of its predecessor gets the staging / record / summary buffers of the previous sample() call back instead of
+# going through cudaMalloc again (a fresh stream per engine did, on every call)
+_STREAMS = {}
+
+
+def _engine_stream(torch, device, slot):
+    key = (str(device), slot)
+    st = _STREAMS.get(key)
+    if st is None:
+        st = _STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _torch():
@@ -68,7 +87,7 @@ class DeviceEngine:
         self.eta_dim = self.q if self.q else self.n
         self.icar_bw = int(problem.get('icar_bw', 0))
         with torch.cuda.device(self.device):
-            self.stream = torch.cuda.Stream(device=self.device)
+            self.stream = _engine_stream(torch, self.device, self.slot)
             dev = {}
 
             def up(name, arr, dtype):
@@ -180,15 +199,25 @@ class DeviceEngine:
             hv = host.numpy()
             for arr, o in zip(parts, offsets):
                 hv[o:o + arr.size] = arr.reshape(-1)
+            t1a = _time.perf_counter()
             dev = host.to(self.device, non_blocking=True)
+            t1b = _time.perf_counter()
             self.h2d_bytes += off * 8
             _lib.check(self.lib.occu_reset(self.handle, self.stream.cuda_stream), 'occu_reset')
+            t1c = _time.perf_counter()
             for (field, _), o in zip(fields, offsets):
                 _lib.check(self.lib.occu_set_field(self.handle, field, dev.data_ptr() + 8 * o, self.stream.cuda_stream),
                            'occu_set_field')
             t2 = _time.perf_counter()
             self.stream.synchronize()   # the staging buffer is free again after this
-        self.setup_seconds.update(start_pin=t1 - t0, start_enqueue=t2 - t1, start_sync=_time.perf_counter() - t2)
+        self.setup_seconds.update(start_pin=t1 - t0, start_pack=t1a - t1, start_h2d=t1b - t1a, start_reset=t1c - t1b,
+                                  start_scatter=t2 - t1c, start_sync=_time.perf_counter() - t2)
+
+    def draw_start(self, seed, eta_scale=1.0, centre_eta=False):
+        """Default start values drawn on the device (include/occu_b200.h: occu_draw_start); nothing crosses PCIe."""
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.occu_draw_start(self.handle, int(seed) & (2**64 - 1), float(eta_scale), int(bool(centre_eta)),
+                                                self.stream.cuda_stream), 'occu_draw_start')
 
     # ---- sampling ------------------------------------------------------------------------------
     def alloc_record(self, capacity):
@@ -246,6 +275,30 @@ class DeviceEngine:
                                                          t.data_ptr(), self.stream.cuda_stream), 'occu_chain_summaries')
                 out[name] = t
             self.stream.synchronize()
+        return out
+
+    def to_host(self, tensors):
+        """Host (NumPy) copies of float64 device tensors: one packed transfer into the cached page-locked staging buffer on
+        the engine's stream, one synchronisation, then a host copy of each part (the staging buffer is reused by the next
+        call).  Pageable ``tensor.cpu()`` copies cost several times as much for the few MB a short run returns."""
+        torch = self.torch
+        counts = [int(t.numel()) for t in tensors]
+        total = sum(-(-c // 8) * 8 for c in counts)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            if total * 8 > _D2H_STAGING_MAX or any(t.dtype != torch.float64 for t in tensors):
+                self.stream.synchronize()
+                out = [t.cpu().numpy() for t in tensors]
+            else:
+                stage = _pinned_buffer(torch, self.device, self.slot, max(total, 1), kind='d2h')
+                views, off = [], 0
+                for t, c in zip(tensors, counts):
+                    dst = stage[off:off + c].view(t.shape)
+                    dst.copy_(t, non_blocking=True)
+                    views.append(dst)
+                    off += -(-c // 8) * 8
+                self.stream.synchronize()
+                out = [v.numpy().copy() for v in views]
+        self.d2h_bytes += 8 * sum(counts)
         return out
 
     @property

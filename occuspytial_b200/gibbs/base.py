@@ -156,14 +156,17 @@ class GibbsBase:
         return out
 
     _START_BLOCK = 128   # chains per start-value generator
+    _DEFAULT_START = (1.0, True)   # (eta_scale, centre_eta) of occu_draw_start: eta ~ N(0, I_n) minus its mean (base.py:201-203)
 
     def _start_arrays_range(self, seed, lo, hi, start):
-        """Start values of the global chains [lo, hi).  Default starts come from one counter-based generator per block
+        """Host-side start values of the global chains [lo, hi) (for engines driven by hand; ``sample()`` draws its
+        default starts on the device, occu_draw_start).  Default starts come from one counter-based generator per block
         of 128 chains, keyed by (seed, block): a shard draws only the blocks it overlaps, and a chain's start value
         does not depend on how the job is sharded over devices or ranks."""
         if start is not None:
             return self._start_arrays(hi - lo, start)
         B = self._START_BLOCK
+
         parts = []
         for blk in range(lo // B, -(-hi // B)):
             rng = np.random.Generator(np.random.Philox(key=[seed & (2**64 - 1), blk]))
@@ -299,18 +302,24 @@ class GibbsBase:
             return [None]
         return [torch.device('cuda', i) for i in range(use)]
 
-    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries, slot=0):
+    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries, slot=0,
+                   summaries_to_host=True):
         """Chains [lo, hi) in lock-step on one device.  Returns (host arrays, summary blocks or None, stats)."""
         import time as _time
         import torch
         local = hi - lo
         t_begin = _time.perf_counter()
-        arrays = self._start_arrays_range(seed, lo, hi, start)
+        # start values given by the caller are broadcast to every chain on the host; the default ones are drawn on the
+        # device from Philox blocks keyed by the global chain id (no host generator, no H2D copy)
+        arrays = self._start_arrays(local, start) if start is not None else None
         t_start = _time.perf_counter()
         engine = self._make_engine(local, seed, chain_offset=lo, device=device, pg_fp64=pg_fp64, gram_int8=gram_int8, slot=slot)
         summaries = None
         try:
-            engine.set_start(self._start_to_engine(arrays))
+            if arrays is not None:
+                engine.set_start(self._start_to_engine(arrays))
+            else:
+                engine.draw_start(seed ^ 0x5DEECE66D, *self._DEFAULT_START)
             t_setup = _time.perf_counter()
             draws = size - burnin
             dims = {'alpha': engine.r, 'beta': engine.p, 'tau': 1}
@@ -379,7 +388,21 @@ class GibbsBase:
             if want_summaries and len(bufs) == 1 and filled == draws and draws >= 4:
                 summaries = engine.chain_summaries(bufs[0], draws, _summary_lag(draws))
             t_summ = _time.perf_counter() - t0
-            if filled:
+            if len(bufs) == 1 and filled == draws:
+                # the usual case: one packed copy through page-locked memory brings back the draws and, in a run without
+                # torch.distributed, the summary blocks (under torch.distributed they stay on the device for the all-gather)
+                t0 = _time.perf_counter()
+                names = list(dims)
+                pull = [bufs[0][k] for k in names]
+                if summaries is not None and summaries_to_host:
+                    pull += [summaries[k] for k in names]
+                parts = engine.to_host(pull)
+                for i, k in enumerate(names):
+                    host[k] = parts[i].reshape(shapes[k])
+                if len(parts) > len(names):
+                    summaries = {k: parts[len(names) + i] for i, k in enumerate(names)}
+                t_flush += _time.perf_counter() - t0
+            elif filled:
                 ev = torch.cuda.Event()
                 ev.record(engine.stream)
                 copy_out(bufs[cur], filled, flushed, ev)
@@ -412,8 +435,23 @@ class GibbsBase:
         """
         if self._model is None:
             raise NotImplementedError(f'{self.__class__.__name__} must implement a `step` method.')
+        import gc
         import time as _time
         t_call = _time.perf_counter()
+        # a generational collection of the host program's objects in the middle of a run stalls the thread that feeds the
+        # launch queue for milliseconds (measured: benchmarks/e2e_breakdown.py); the run itself allocates a few dozen
+        # objects, so the collector is paused for its duration
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._run_lockstep_body(t_call, size, burnin, start, chains, progressbar, pos, device, devices, pg_fp64,
+                                           gram_int8)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+
+    def _run_lockstep_body(self, t_call, size, burnin, start, chains, progressbar, pos, device, devices, pg_fp64, gram_int8):
+        import time as _time
         rank, world = dist_info()
         # the same host RNG stream is consumed on every rank: one draw for the device seed
         seed = int(self.rng.integers(0, 2**63 - 1))
@@ -438,7 +476,7 @@ class GibbsBase:
             def job(k):
                 dev, a, b = jobs[k]
                 return self._run_shard(dev, a, b, seed, start, size, burnin, bar if k == 0 else None, pg_fp64, gram_int8,
-                                       want_summaries=True, slot=k)
+                                       want_summaries=True, slot=k, summaries_to_host=world == 1)
             if len(jobs) == 1:
                 results = [job(0)]
             else:
@@ -491,10 +529,11 @@ class GibbsBase:
         def pack(result):    # one tensor per engine: a single copy / a single collective moves all three parameters
             return torch.cat([result[1][k] for k in names], dim=1)
 
-        if world == 1:
+        if world == 1:      # the engines already copied their blocks to the host (_run_shard)
             if not have:
                 return None
-            return split(np.concatenate([pack(r).cpu().numpy() for r in results], axis=0))
+            return {k: (results[0][1][k] if len(results) == 1 else np.concatenate([r[1][k] for r in results], axis=0))
+                    for k in names}
         import torch.distributed as dist
         from .parallel import allgather_summaries
         # every rank must agree on whether the collective runs (a rank that flushed in blocks has no device summaries)

@@ -107,6 +107,8 @@ class LogitRSRGibbs(LogitICARGibbs):
             del self.fixed.tau_shape
             self.fixed.tau_shape = 0.5 + 0.5 * self.fixed.q
 
+    _DEFAULT_START = (5.0, False)   # eta ~ N(0, 25 I_q), not centred (logit.py:464)
+
     def _eta_start(self, chains, rng=None):
         """logit.py:462-466: eta ~ N(0, 25 I_q)."""
         rng = self.rng if rng is None else rng

@@ -49,6 +49,8 @@ class ProbitRSRGibbs(GibbsBase):
             del self.fixed.tau_shape
             self.fixed.tau_shape = 0.5 + 0.5 * self.fixed.q
 
+    _DEFAULT_START = (5.0, False)   # eta ~ N(0, 25 I_q), not centred (probit.py:157)
+
     def _eta_start(self, chains, rng=None):
         rng = self.rng if rng is None else rng
         return rng.normal(scale=5, size=(chains, self.fixed.q))
