@@ -50,11 +50,17 @@ namespace gtc {
 constexpr int SA = 6;             // omega slices (unsigned bytes): 48-bit fixed point of omega / 8
 constexpr int SA_F32 = 4;         // ... of which the first 4 can be non-zero when omega was drawn in FP32 (32-bit fixed point)
 constexpr int SB = GTC_SB;        // Z slices (balanced signed bytes): 6 -> |error| <= 2^-49 c_m per entry, 5 -> 2^-41 c_m
-constexpr int LMAX = 7;           // keep slice pairs with s + t <= LMAX (dropped products are below 2^-56 of the scale)
+#ifndef GTC_LMAX
+#define GTC_LMAX 7
+#endif
+constexpr int LMAX = GTC_LMAX;    // keep slice pairs with s + t <= LMAX (7: dropped products are below 2^-56 of the scale)
 constexpr int NLEV = LMAX - 1;    // levels 2 .. LMAX
 constexpr int BM = 128;           // chains per tile (TMEM lanes)
 constexpr int BK = 64;            // bytes (= int8 elements) of K per stage, one SWIZZLE_64B row
-constexpr int BN_DEFAULT = SB == 6 ? 64 : 80;  // Z columns per tile: NLEV x BN TMEM columns, 3 stages within 227 KB
+#ifndef GTC_BN
+#define GTC_BN (GTC_SB == 6 ? 64 : 80)
+#endif
+constexpr int BN_DEFAULT = GTC_BN;  // Z columns per tile: NLEV x BN TMEM columns, 3 stages within 227 KB
 #ifndef GTC_MAX_STAGES
 #define GTC_MAX_STAGES 4
 #endif

@@ -7,7 +7,7 @@ out=gpurun_out/overlap_probe.jsonl
 for lib in default s3 s2; do
   for prio in 0 1; do
     if [ $lib = default ]; then unset OCCU_B200_LIB; else export OCCU_B200_LIB=$PWD/occuspytial_b200/csrc/variants/liboccu_b200_$lib.so; fi
-    OCCU_GRAM_PRIO=$prio timeout 300 python benchmarks/overlap_probe.py 1 2 4 >> $out 2>> gpurun_out/overlap_probe.err
+    timeout 300 python benchmarks/overlap_probe.py 1 2 4 >> $out 2>> gpurun_out/overlap_probe.err
   done
 done
 unset OCCU_B200_LIB
