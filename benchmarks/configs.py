@@ -22,10 +22,9 @@ sys.path.insert(0, ROOT)
 def run(name, sampler, chains, steps, warmup, note):
     import torch
     seed = 1
-    start = sampler._start_to_engine(sampler._start_arrays(chains, None))
     t0 = time.perf_counter()
     eng = sampler._make_engine(chains, seed)
-    eng.set_start(start)
+    eng.draw_start(seed, *sampler._DEFAULT_START)
     setup_s = time.perf_counter() - t0
     fails = eng.sweep(warmup)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
