@@ -365,7 +365,7 @@ def run_b200(args):
                'r_hat_tau_from_device_summaries': float(post.summary.loc['tau', 'r_hat']),
                'note': f'median of three timed sampler.sample({iters}, burnin={args.warmup}, chains={chains_total}) calls (all three '
                        'listed in timed_calls_s), wall clock incl. problem upload, start values, all iterations, per-chain '
-                       'summary blocks (all-gathered over the ranks) and the copy of the recorded draws to host; one '
+                       'summary blocks (all-gathered over the ranks, reduced over the chains on the device) and the copy of the recorded draws to host; one '
                        'untimed call of the same API and size before them'}
 
     if rank != 0:

@@ -25,30 +25,54 @@ def summaries_from_draws(x, max_lag):
     return out
 
 
-def split_rhat(summ, draws):
-    """Classic split-R-hat (Gelman et al. 2013) from summary blocks of shape (chains, 6 + L + 1)."""
+REDUCED_HEAD = 5   # leading entries of a reduced block; the mean autocovariances follow
+
+
+def reduce_blocks(summ):
+    """Cross-chain reduction of per-chain summary blocks ``(chains, ..., 6 + L + 1)`` to ``(..., 5 + L + 1)``:
+    ``{mean of the chain means, their variance (ddof = 1; 0 for one chain), sum of M2, mean M2 of the 2 x chains
+    half-chains, variance (ddof = 1) of the half-chain means, mean autocovariances 0..L}`` -- all that split-R-hat, the
+    ESS and the pooled moments need.  Works on a NumPy array or a torch tensor (any device): a multi-GPU run reduces
+    the all-gathered blocks where they are and brings back only this."""
+    if isinstance(summ, np.ndarray):
+        chains = summ.shape[0]
+        out = np.empty(summ.shape[1:-1] + (REDUCED_HEAD + summ.shape[-1] - 6,))
+        out[..., 0] = summ[..., 0].mean(axis=0)
+        out[..., 1] = summ[..., 0].var(axis=0, ddof=1) if chains > 1 else 0.0
+        out[..., 2] = summ[..., 1].sum(axis=0)
+        out[..., 3] = np.concatenate([summ[..., 3], summ[..., 5]], axis=0).mean(axis=0)
+        out[..., 4] = np.concatenate([summ[..., 2], summ[..., 4]], axis=0).var(axis=0, ddof=1)
+        out[..., REDUCED_HEAD:] = summ[..., 6:].mean(axis=0)
+        return out
+    import torch
+    chains = summ.shape[0]
+    head = [summ[..., 0].mean(dim=0),
+            summ[..., 0].var(dim=0, unbiased=True) if chains > 1 else torch.zeros_like(summ[0, ..., 0]),
+            summ[..., 1].sum(dim=0),
+            torch.cat([summ[..., 3], summ[..., 5]], dim=0).mean(dim=0),
+            torch.cat([summ[..., 2], summ[..., 4]], dim=0).var(dim=0, unbiased=True)]
+    return torch.cat([torch.stack(head, dim=-1), summ[..., 6:].mean(dim=0)], dim=-1)
+
+
+def split_rhat_reduced(red, draws):
+    """Classic split-R-hat (Gelman et al. 2013) from a reduced block (``reduce_blocks``)."""
     half = draws // 2
-    means = np.concatenate([summ[:, 2], summ[:, 4]])
-    variances = np.concatenate([summ[:, 3], summ[:, 5]]) / (half - 1)
-    W = variances.mean()
-    B = half * means.var(ddof=1)
+    W = red[3] / (half - 1)
+    B = half * red[4]
     var_plus = (half - 1) / half * W + B / half
     return float(np.sqrt(var_plus / W)) if W > 0 else float('nan')
 
 
-def ess(summ, draws):
-    """Multi-chain ESS with Geyer's initial-monotone-sequence truncation from the autocovariances."""
-    chains = summ.shape[0]
-    means = summ[:, 0]
-    acov = summ[:, 6:]                        # (chains, L + 1), biased (1/draws) estimator
-    chain_var = acov[:, 0] * draws / (draws - 1)
-    W = chain_var.mean()
+def ess_reduced(red, draws, chains):
+    """Multi-chain ESS with Geyer's initial-monotone-sequence truncation from the mean autocovariances of a reduced block."""
+    acov = np.asarray(red[REDUCED_HEAD:], dtype=np.float64)   # biased (1/draws) estimator, mean over chains
+    W = acov[0] * draws / (draws - 1)
     var_plus = W * (draws - 1) / draws
     if chains > 1:
-        var_plus += means.var(ddof=1)
+        var_plus += red[1]
     if not var_plus > 0:
         return float('nan')
-    rho = 1.0 - (W - acov.mean(axis=0)) / var_plus
+    rho = 1.0 - (W - acov) / var_plus
     rho[0] = 1.0
     L = rho.size
     tau_hat = -1.0
@@ -66,6 +90,24 @@ def ess(summ, draws):
     return float(chains * draws / tau_hat)
 
 
+def pooled_moments_reduced(red, draws, chains):
+    """Pooled mean and standard deviation (ddof = 1) of all draws from a reduced block (equal chain lengths)."""
+    m2 = red[2] + draws * (chains - 1) * red[1]
+    total = chains * draws
+    return float(red[0]), float(np.sqrt(m2 / (total - 1))) if total > 1 else float('nan')
+
+
+def split_rhat(summ, draws):
+    """Split-R-hat from per-chain summary blocks of shape (chains, 6 + L + 1)."""
+    return split_rhat_reduced(reduce_blocks(np.asarray(summ, dtype=np.float64)), draws)
+
+
+def ess(summ, draws):
+    """Multi-chain ESS from per-chain summary blocks of shape (chains, 6 + L + 1)."""
+    summ = np.asarray(summ, dtype=np.float64)
+    return ess_reduced(reduce_blocks(summ), draws, summ.shape[0])
+
+
 def hdi(x, prob=0.94):
     """Highest-density interval of a flat sample."""
     x = np.sort(np.asarray(x).ravel())
@@ -80,19 +122,60 @@ def hdi(x, prob=0.94):
 
 def pooled_moments(summ, draws):
     """Pooled mean and standard deviation (ddof = 1) of all draws from the per-chain blocks (equal chain lengths)."""
-    chains = summ.shape[0]
-    mean = summ[:, 0].mean()
-    m2 = summ[:, 1].sum() + draws * ((summ[:, 0] - mean) ** 2).sum()
-    total = chains * draws
-    return float(mean), float(np.sqrt(m2 / (total - 1))) if total > 1 else float('nan')
+    summ = np.asarray(summ, dtype=np.float64)
+    return pooled_moments_reduced(reduce_blocks(summ), draws, summ.shape[0])
+
+
+class ChainSummaries:
+    """Summary blocks of all chains of a run (``{name: (chains, dim, 6 + L + 1)}``) and their cross-chain reduction.
+
+    The reduction (``reduced[name]``: ``(dim, 5 + L + 1)``, a few hundred numbers) is computed where the blocks are --
+    on the device that recorded the draws or, in a multi-process run, on the all-gathered tensor -- and is all that
+    ``PosteriorParameter.summary`` needs.  The per-chain blocks themselves stay where they are until somebody indexes
+    this object (``summaries['tau']``), which copies them to the host once."""
+
+    def __init__(self, names, dims, chains, packed):
+        self.names = list(names)
+        self.dims = dict(zip(self.names, dims))
+        self.chains = int(chains)
+        self._packed = packed            # (chains, sum(dims), 6 + L + 1): NumPy array or torch tensor (any device)
+        red = reduce_blocks(packed)
+        if not isinstance(red, np.ndarray):
+            red = red.cpu().numpy()
+        self.reduced = self._split(red, axis=0)
+        self._blocks = None
+
+    def _split(self, arr, axis):
+        out, o = {}, 0
+        for k in self.names:
+            d = self.dims[k]
+            out[k] = arr[o:o + d] if axis == 0 else arr[:, o:o + d]
+            o += d
+        return out
+
+    def _load(self):
+        if self._blocks is None:
+            arr = self._packed if isinstance(self._packed, np.ndarray) else self._packed.cpu().numpy()
+            self._blocks = self._split(arr, axis=1)
+            self._packed = arr
+        return self._blocks
+
+    def __getitem__(self, name):
+        return self._load()[name]
+
+    def __contains__(self, name):
+        return name in self.dims
+
+    def keys(self):
+        return list(self.names)
 
 
 def summary_frame(data, max_lag=None, summaries=None):
     """pandas.DataFrame with arviz-like columns for ``{name: (chains, draws[, dim])}``.
 
-    ``summaries``: optional per-chain summary blocks ``{name: (chains, dim, 6 + L + 1)}`` (device-computed, possibly
-    covering more chains than ``data`` holds locally); mean, sd, mcse_mean, ess_bulk and r_hat are then derived from
-    them, only the HDI is taken from the draws in ``data``."""
+    ``summaries``: optional :class:`ChainSummaries` (or plain per-chain summary blocks ``{name: (chains, dim, 6 + L + 1)}``),
+    device-computed and possibly covering more chains than ``data`` holds locally; mean, sd, mcse_mean, ess_bulk and
+    r_hat are then derived from their cross-chain reduction, only the HDI is taken from the draws in ``data``."""
     import pandas as pd
     rows, index = [], []
     for name, arr in data.items():
@@ -101,19 +184,26 @@ def summary_frame(data, max_lag=None, summaries=None):
             arr = arr[:, :, None]
         chains, draws, dim = arr.shape
         L = min(draws - 1, 250) if max_lag is None else max_lag
-        blocks = None if summaries is None or name not in summaries else np.asarray(summaries[name])
+        reduced = total_chains = None
+        if summaries is not None and name in summaries:
+            if isinstance(summaries, ChainSummaries):
+                reduced, total_chains = summaries.reduced[name], summaries.chains
+            else:   # plain per-chain blocks
+                blocks = np.asarray(summaries[name], dtype=np.float64)
+                reduced, total_chains = reduce_blocks(blocks), blocks.shape[0]
         for k in range(dim):
             x = arr[:, :, k]
-            if blocks is not None:
-                summ = blocks[:, k, :]
-                mean, sd = pooled_moments(summ, draws)
+            if reduced is not None:
+                red, nch = reduced[k], total_chains
+                mean, sd = pooled_moments_reduced(red, draws, nch)
             else:
-                summ = summaries_from_draws(x, L) if draws > 3 else None
+                red = reduce_blocks(summaries_from_draws(x, L)) if draws > 3 else None
+                nch = chains
                 mean, sd = x.mean(), x.std(ddof=1) if x.size > 1 else np.nan
             lo, hi = hdi(x) if x.size else (np.nan, np.nan)
-            if summ is not None:
-                n_eff = ess(summ, draws)
-                rhat = split_rhat(summ, draws) if draws >= 4 else np.nan
+            if red is not None:
+                n_eff = ess_reduced(red, draws, nch)
+                rhat = split_rhat_reduced(red, draws) if draws >= 4 else np.nan
             else:
                 n_eff, rhat = np.nan, np.nan
             mcse = sd / np.sqrt(n_eff) if n_eff and n_eff > 0 else np.nan

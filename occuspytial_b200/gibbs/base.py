@@ -6,6 +6,8 @@ What moved to the device: everything inside ``for i in range(size): self.step();
 (base.py:236-239) -- the loop runs in C++/CUDA for all chains in lock-step and ``Chain`` objects are
 zero-copy views of the block of draws copied back once per flush.
 """
+import contextlib
+
 import numpy as np
 from scipy.sparse import csc_matrix, isspmatrix_csc
 from tqdm.auto import tqdm
@@ -302,8 +304,7 @@ class GibbsBase:
             return [None]
         return [torch.device('cuda', i) for i in range(use)]
 
-    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries, slot=0,
-                   summaries_to_host=True):
+    def _run_shard(self, device, lo, hi, seed, start, size, burnin, bar, pg_fp64, gram_int8, want_summaries, slot=0):
         """Chains [lo, hi) in lock-step on one device.  Returns (host arrays, summary blocks or None, stats)."""
         import time as _time
         import torch
@@ -389,18 +390,13 @@ class GibbsBase:
                 summaries = engine.chain_summaries(bufs[0], draws, _summary_lag(draws))
             t_summ = _time.perf_counter() - t0
             if len(bufs) == 1 and filled == draws:
-                # the usual case: one packed copy through page-locked memory brings back the draws and, in a run without
-                # torch.distributed, the summary blocks (under torch.distributed they stay on the device for the all-gather)
+                # the usual case: one packed copy through page-locked memory brings back the draws; the summary blocks stay
+                # on the device (their cross-chain reduction is all `summary` needs, diagnostics.ChainSummaries)
                 t0 = _time.perf_counter()
                 names = list(dims)
-                pull = [bufs[0][k] for k in names]
-                if summaries is not None and summaries_to_host:
-                    pull += [summaries[k] for k in names]
-                parts = engine.to_host(pull)
+                parts = engine.to_host([bufs[0][k] for k in names])
                 for i, k in enumerate(names):
                     host[k] = parts[i].reshape(shapes[k])
-                if len(parts) > len(names):
-                    summaries = {k: parts[len(names) + i] for i, k in enumerate(names)}
                 t_flush += _time.perf_counter() - t0
             elif filled:
                 ev = torch.cuda.Event()
@@ -476,7 +472,7 @@ class GibbsBase:
             def job(k):
                 dev, a, b = jobs[k]
                 return self._run_shard(dev, a, b, seed, start, size, burnin, bar if k == 0 else None, pg_fp64, gram_int8,
-                                       want_summaries=True, slot=k, summaries_to_host=world == 1)
+                                       want_summaries=True, slot=k)
             if len(jobs) == 1:
                 results = [job(0)]
             else:
@@ -509,31 +505,29 @@ class GibbsBase:
         return out
 
     def _gather_summaries(self, results, chains, local, draws, dims, world):
-        """Global per-chain summary blocks {name: ndarray (chains, dim, 6 + L + 1)} or None.  Device tensors of the
-        local engines are concatenated; under torch.distributed they are all-gathered (NCCL: the blocks never leave
-        the devices until the gathered result is read)."""
+        """:class:`~occuspytial_b200.diagnostics.ChainSummaries` of ALL chains of the job, or None.  The per-chain blocks
+        of the local engines are concatenated on the first engine's device; under torch.distributed they are
+        all-gathered (NCCL).  Either way they are reduced over the chains where they are: only the reduction -- a few
+        hundred numbers -- crosses PCIe here, the blocks follow if somebody asks for them."""
         if draws < 4:
             return None
         have = bool(results) and all(r[1] is not None for r in results)
         import torch
+        from ..diagnostics import ChainSummaries
         names = list(dims)
         widths = [dims[k] for k in names]
 
-        def split(packed):   # (chains, sum(dims), W) -> {name: (chains, dim, W)}
-            out, o = {}, 0
-            for k, d in zip(names, widths):
-                out[k] = packed[:, o:o + d]
-                o += d
-            return out
+        def pack(result, dev):    # one tensor per engine: a single collective moves all three parameters
+            return torch.cat([result[1][k].to(dev) for k in names], dim=1)
 
-        def pack(result):    # one tensor per engine: a single copy / a single collective moves all three parameters
-            return torch.cat([result[1][k] for k in names], dim=1)
-
-        if world == 1:      # the engines already copied their blocks to the host (_run_shard)
+        if world == 1:
             if not have:
                 return None
-            return {k: (results[0][1][k] if len(results) == 1 else np.concatenate([r[1][k] for r in results], axis=0))
-                    for k in names}
+            dev = results[0][1][names[0]].device
+            ctx = torch.cuda.device(dev) if dev.type == 'cuda' else contextlib.nullcontext()
+            with ctx:
+                packed = torch.cat([pack(r, dev) for r in results], dim=0)
+                return ChainSummaries(names, widths, chains, packed)
         import torch.distributed as dist
         from .parallel import allgather_summaries
         # every rank must agree on whether the collective runs (a rank that flushed in blocks has no device summaries)
@@ -545,10 +539,10 @@ class GibbsBase:
             return None
         W = 6 + _summary_lag(draws) + 1
         if have:
-            t = torch.cat([pack(r) for r in results], dim=0)
+            t = torch.cat([pack(r, dev) for r in results], dim=0)
         else:
             t = torch.zeros((0, sum(widths), W), dtype=torch.float64, device=dev)
-        return split(allgather_summaries(t, chains).cpu().numpy())
+        return ChainSummaries(names, widths, chains, allgather_summaries(t, chains))
 
     def _run(self, size, burnin=0, start=None, chains=2, progressbar=True, pos=0):
         """Single-chain entry point kept for API compatibility (base.py:214-241)."""

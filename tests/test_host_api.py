@@ -120,6 +120,48 @@ def test_diagnostics_against_known_cases():
     assert split_rhat(summaries_from_draws(shifted, 10), 2000) > 1.5
 
 
+def test_reduced_summary_blocks_and_lazy_chain_summaries():
+    """Cross-chain reduction of the per-chain blocks (diagnostics.reduce_blocks: NumPy and torch give the same numbers)
+    against the textbook formulas evaluated on the draws, and ChainSummaries, which keeps the blocks where they are."""
+    import torch
+    from occuspytial_b200 import posterior
+    from occuspytial_b200.diagnostics import (ChainSummaries, summaries_from_draws, reduce_blocks, split_rhat_reduced,
+                                              pooled_moments_reduced, ess_reduced, ess, summary_frame)
+    rng = np.random.default_rng(5)
+    chains, draws, L = 7, 400, 60
+    x = np.zeros((chains, draws, 2))
+    e = rng.normal(size=x.shape)
+    for t in range(1, draws):
+        x[:, t] = 0.7 * x[:, t - 1] + e[:, t]
+    x[:, :, 1] += 0.3 * np.arange(chains)[:, None]
+    blocks = np.stack([summaries_from_draws(x[:, :, k], L) for k in range(2)], axis=1)      # (chains, 2, 6 + L + 1)
+    red = reduce_blocks(blocks)
+    np.testing.assert_allclose(reduce_blocks(torch.from_numpy(blocks)).numpy(), red, rtol=1e-13, atol=1e-15)
+    half = draws // 2
+    for k in range(2):
+        xs = x[:, :, k]
+        halves = np.concatenate([xs[:, :half], xs[:, draws - half:]])
+        Wv, B = halves.var(axis=1, ddof=1).mean(), half * halves.mean(axis=1).var(ddof=1)
+        rhat = np.sqrt(((half - 1) / half * Wv + B / half) / Wv)
+        np.testing.assert_allclose(split_rhat_reduced(red[k], draws), rhat, rtol=1e-12)
+        mean, sd = pooled_moments_reduced(red[k], draws, chains)
+        np.testing.assert_allclose([mean, sd], [xs.mean(), xs.std(ddof=1)], rtol=1e-12)
+        np.testing.assert_allclose(ess_reduced(red[k], draws, chains), ess(blocks[:, k], draws), rtol=1e-13)
+    packed = torch.from_numpy(np.concatenate([blocks, blocks[:, :1]], axis=1))               # 'a' (dim 2) and 't' (dim 1)
+    cs = ChainSummaries(['a', 't'], [2, 1], chains, packed)
+    assert cs._blocks is None and 'a' in cs and 'z' not in cs and cs.keys() == ['a', 't']
+    np.testing.assert_allclose(cs.reduced['a'], red, rtol=1e-13, atol=1e-15)
+    if posterior.az is None:
+        data = {'a': x, 't': x[:, :, 0]}
+        lazy = summary_frame(data, summaries=cs)
+        assert cs._blocks is None                       # the summary did not need the per-chain blocks
+        plain = summary_frame(data, max_lag=L)
+        np.testing.assert_allclose(lazy[['mean', 'sd', 'ess_bulk', 'r_hat']].to_numpy(),
+                                   plain[['mean', 'sd', 'ess_bulk', 'r_hat']].to_numpy(), rtol=1e-10)
+    assert cs['a'].shape == (chains, 2, 6 + L + 1) and cs['t'].shape == (chains, 1, 6 + L + 1) and cs._blocks is not None
+    np.testing.assert_array_equal(cs['a'], blocks)
+
+
 Q, W, X, y, *_ = (None,) * 5
 
 
