@@ -51,6 +51,7 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--c5-chains', default='512,2048,8192,32768')
+    ap.add_argument('--c4-chains', default='1024', help='chain counts of config 4 (1024 = BASELINE; others show how the solve scales)')
     args = ap.parse_args()
     only = set(args.only.split(','))
     from occuspytial_b200 import LogitRSRGibbs, ProbitRSRGibbs, LogitICARGibbs
@@ -71,7 +72,9 @@ def main():
     if 'c4' in only:
         Q, W, X, y, *_ = make_data(n=2500, min_v=2, max_v=8, lattice=(50, 50), random_state=0)
         s = LogitICARGibbs(Q, W, X, y, random_state=10)
-        run('c4', s, 1024, args.steps, args.warmup, f'PGGibbs full ICAR n=2500 (50x50), half bandwidth {s._band()[1]}, 1024 chains')
+        for chains in (int(c) for c in args.c4_chains.split(',')):
+            run('c4' if chains == 1024 else f'c4_{chains}', s, chains, args.steps, args.warmup,
+                f'PGGibbs full ICAR n=2500 (50x50), half bandwidth {s._band()[1]}, {chains} chains')
     if 'c5' in only:
         t0 = time.perf_counter()
         Q, W, X, y, *_ = make_data(n=50000, min_v=2, max_v=8, lattice=(200, 250), random_state=0)

@@ -35,6 +35,16 @@
 // L_below' [x zv m] is a chain of DMMAs split over the four warps, three lanes finish the 8 x 8 triangular solves.
 // ------------------------------------------------------------------------------------------------
 constexpr int ICARW_THREADS = 128;
+// -DICARW_PROF: cycle counts per phase and warp of chain 0, printed at the end of the kernel (measurement builds only)
+#ifdef ICARW_PROF
+#define ICARW_T(var) const long long var = clock64()
+#define ICARW_SET(var) var = clock64()
+#define ICARW_ACC(acc, t1, t0) acc += (t1) - (t0)
+#else
+#define ICARW_T(var)
+#define ICARW_SET(var)
+#define ICARW_ACC(acc, t1, t0)
+#endif
 
 // window tiles per side: the smallest compiled instance (2, 4, 6, 8: fully unrolled tile loops, constant shared-memory
 // offsets) that covers bw + 8 rows, else the exact count with run-time loops (template argument 0)
@@ -66,6 +76,22 @@ __device__ __forceinline__ void icarw_cp8(double* dst, const double* src, bool o
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(src), "r"(bytes));
 }
 
+// 16-byte variant (two doubles; both addresses 16-byte aligned)
+__device__ __forceinline__ void icarw_cp16(double* dst, const double* src, bool ok) {
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sdst), "l"(src), "r"(bytes));
+}
+// one band row / factor column of `count` doubles by a warp, all of it valid or none (zero fill): pairs when the rows
+// are 16-byte aligned (count even: every row of a [.][count] array then starts on a 16-byte boundary)
+__device__ __forceinline__ void icarw_stage_line(double* dst, const double* src, int count, bool ok, int lane) {
+    if ((count & 1) == 0) {
+        for (int e = 2 * lane; e < count; e += 64) icarw_cp16(dst + e, src + e, ok);
+    } else {
+        for (int e = lane; e < count; e += 32) icarw_cp8(dst + e, src + e, ok);
+    }
+}
+
 // compact non-zero offsets of every band row of Q (set-up, once): qnz[i][0] = count (255: too many), then the offsets
 __global__ void icar_nonzeros_kernel(const double* __restrict__ Qband, int n, int W1, uint8_t* __restrict__ qnz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +121,20 @@ __device__ __forceinline__ double cta4_sum(double val, double* red) {
     return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
+// 1 / sqrt(a) for a pivot of Lambda (positive, far inside the FP32 range: tau Q_ii + omega_i): the FP32 hardware
+// approximation (relative error < 2^-22) refined by two Newton steps y <- y (3/2 - a/2 y^2) in FP64 (2^-44, then FP64
+// rounding).  Ten dependent instructions on the one chain of the factorisation that cannot be overlapped.
+__device__ __forceinline__ double icarw_rsqrt(double a) {
+    float yf;
+    const float af = (float)a;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(af));
+    double y = (double)yf;
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 // Cholesky factorisation of an 8 x 8 block by ONE WARP: lane a < 8 holds row a of the lower triangle (row[b], b <= a);
 // column j is scaled by 1 / sqrt(pivot) (rsqrt, no divide) and exchanged by shuffles for the rank-1 update.  Writes the
 // factor (row-major 8 x 8, lower) and the reciprocal pivots to shared memory.  Returns false on a non-positive pivot.
@@ -109,7 +149,7 @@ __device__ __forceinline__ bool icarw_chol8(const double* __restrict__ D, double
     for (int j = 0; j < 8; j++) {
         const double piv = __shfl_sync(0xffffffffu, row[j], j);
         if (!(piv > 0.0)) ok = false;
-        const double ri = rsqrt(piv);
+        const double ri = icarw_rsqrt(piv);
         const double laj = (a == j) ? piv * ri : row[j] * ri;
         row[j] = laj;
         if (lane == j) invs[j] = ri;
@@ -125,6 +165,43 @@ __device__ __forceinline__ bool icarw_chol8(const double* __restrict__ D, double
             if (b <= a) Lds[a * 8 + b] = row[b];
     }
     return ok;
+}
+
+// Rank-8 trailing update of one of the three update warps (HW = 0..2) for a compiled window size: the tiles that stay,
+// named by their slot distances (ra, rb) from the pivot slot, 1 <= rb <= ra <= NT - 1 without (1, 1) (the next pivot
+// block, which warp 0 updates and factorises), are numbered row by row and dealt 3 : 3 : 4 to the warps -- the last warp
+// has no window rows to solve up to W = 64.  The list is a compile-time constant, so a warp executes exactly its own
+// tiles: a lone warp issues an instruction every ~6 cycles, and the earlier version, which walked all NT (NT + 1) / 2
+// stored pairs under predicates, spent 342 issue slots per step on the critical path of the factorisation.
+// tile (hi, lo) -= P_hi P_lo' with hi / lo the larger / smaller SLOT of the pair (only slot pairs a >= b are stored);
+// the A and B fragments of a slot are the same two panel entries, the minus sign is an operand modifier of the DMMA.
+template <int NT, int HW>
+__device__ __forceinline__ void icarw_update_tiles(double* __restrict__ Ts, const double* __restrict__ Ps, int Wp, int cs,
+                                                   int g, int t4) {
+    int slot[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int r = 1; r < NT; r++) {
+        const int sl = cs + r;
+        slot[r] = sl >= NT ? sl - NT : sl;
+    }
+    const double* p0 = Ps + t4 * Wp + g;
+    const double* p1 = Ps + (4 + t4) * Wp + g;
+    int k = 0;
+#pragma unroll
+    for (int ra = 2; ra < NT; ra++) {
+#pragma unroll
+        for (int rb = 1; rb <= ra; rb++, k++) {
+            const int owner = (k % 10) < 4 ? 2 : ((k % 10) < 7 ? 0 : 1);
+            if (owner != HW) continue;
+            const int hi = max(slot[ra], slot[rb]), lo = min(slot[ra], slot[rb]);
+            const double a0 = p0[8 * hi], a1 = p1[8 * hi], b0 = p0[8 * lo], b1 = p1[8 * lo];
+            double2* cp = reinterpret_cast<double2*>(Ts + (hi * (hi + 1) / 2 + lo) * 64 + g * 8 + 2 * t4);
+            double2 cv = *cp;
+            dgemm::dmma884(cv.x, cv.y, -a0, b0);
+            dgemm::dmma884(cv.x, cv.y, -a1, b1);
+            *cp = cv;
+        }
+    }
 }
 
 template <int NT_T>
@@ -252,12 +329,37 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
         for (int rr = first; rr < 8; rr += step) {
             const int i = base + rr;
             const double* srow = v.Qband + (size_t)(i < n ? i : 0) * W1;
-            for (int d = lane; d < W1; d += 32) icarw_cp8(dst + rr * W1p + d, srow + d, i < n && d <= i);
+            if (i >= w) {   // the whole band row exists (all rows but the first bw)
+                icarw_stage_line(dst + rr * W1p, srow, W1, i < n, lane);
+            } else {
+                for (int d = lane; d < W1; d += 32) icarw_cp8(dst + rr * W1p + d, srow + d, d <= i);
+            }
         }
         if (first == 0 && lane < 16) {
             const int rr = lane & 7, i = base + rr;
             const double* srcv = lane < 8 ? om_c : xs;
             icarw_cp8(dst + 8 * W1p + (lane < 8 ? 0 : 8) + rr, i < n ? srcv + i : srcv, i < n);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    // the same for a group of complete band rows (base >= bw; rows past n are zero-filled) when the rows are 16-byte
+    // aligned: four lanes per row, 16-byte pieces -- ~40 instructions instead of ~400 for the warp that issues them
+    auto stage_rows_fast = [&](int base) {
+        const int rr = lane >> 2, i = base + rr, q4 = 2 * (lane & 3);
+        const bool ok = i < n;
+        const double* src = v.Qband + (size_t)(ok ? i : 0) * W1 + q4;
+        double* dst = stg + rr * W1p + q4;
+        if (NT_T > 0) {   // W1 <= 8 NT - 7: at most NT pieces per lane, constant offsets
+#pragma unroll
+            for (int it = 0; it < (NT_T > 0 ? NT_T : 1); it++)
+                if (q4 + 8 * it < W1) icarw_cp16(dst + 8 * it, src + 8 * it, ok);
+        } else {
+            for (int e = q4; e < W1; e += 8, dst += 8, src += 8) icarw_cp16(dst, src, ok);
+        }
+        if (lane < 16) {
+            const int r2 = lane & 7, i2 = base + r2;
+            const double* srcv = lane < 8 ? om_c : xs;
+            icarw_cp8(stg + 8 * W1p + (lane < 8 ? 0 : 8) + r2, i2 < n ? srcv + i2 : srcv, i2 < n);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -311,42 +413,48 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
         if (warp == ((a + 1) & 3)) fill_rhs(stg, a, 8 * a);
         __syncthreads();
     }
-    // factor of the first pivot block
+    // factor of the first pivot block; the rows that enter in step 0 (group NT) start their way to shared memory
     if (warp == 0) {
         if (!icarw_chol8(Ts, Lds, invs, lane)) piv_ok = 0;
+    } else if (warp == 3) {
+        stage_rows(8 * NT, 0, 1);
     }
     __syncthreads();
 
     // ---- blocked factorisation + fused forward substitutions ----
     const int nsteps = n8 / 8;
+    const int rf_rows = g * W1p + g - 2 * t4, rf_cols = 2 * t4 * W1p + 2 * t4 - g;   // refill: lane offsets into the staged rows
+#ifdef ICARW_PROF
+    long long pr_row = 0, pr_b1 = 0, pr_upd = 0, pr_b2 = 0, pr_chol = 0, pr_refill = 0, pr_nb = 0, pr_resid = 0, pr_dmma = 0;
+    const long long pr_t_fwd0 = clock64();
+#endif
     for (int m = 0; m < nsteps; m++) {
         if (!piv_ok) break;   // uniform (read after a barrier)
         const int cs = m % NT, j0 = 8 * m;
         const int cs1 = cs + 1 == NT ? 0 : cs + 1;   // the next pivot slot
         // ===== row phase =====
+        ICARW_T(pt0);
         if (warp == 0) {
-            // entering rows of this step (group m + NT): staged now, consumed by the refill after the barrier
-            stage_rows(8 * (m + NT), 0, 1);
-            // the two right-hand sides of the pivot rows: y_r = L_JJ^-1 rhs_r (lane r)
-            if (lane < 2) {
-                double yv[8];
+            // the two right-hand sides of the pivot rows, y_r = L_JJ^-1 rhs_r: lane 8 r + b holds entry b of right-hand
+            // side r; column by column the solved entry is broadcast by a shuffle and eliminated from the entries below it
+            // (8 dependent shuffle + multiply-add steps instead of 36 in a lane that solves a whole column alone)
+            {
+                const int b = lane & 7, r = (lane >> 3) & 1;
+                double t = rhs[r * W + 8 * cs + b];
+                double yv = 0.0;
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    double t = rhs[lane * W + 8 * cs + b];
-#pragma unroll
-                    for (int k = 0; k < b; k++) t = fma(-yv[k], Lds[b * 8 + k], t);
-                    yv[b] = t * invs[b];
+                for (int j = 0; j < 8; j++) {
+                    const double yj = __shfl_sync(0xffffffffu, t, (lane & 24) | j) * invs[j];
+                    if (b == j) yv = yj;
+                    if (b > j) t = fma(-yj, Lds[b * 8 + j], t);
                 }
-                double* dstg = lane == 0 ? yb : y1;
-#pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    yvs[lane * 8 + b] = yv[b];
-                    if (j0 + b < n) dstg[j0 + b] = yv[b];
+                if (lane < 16) {
+                    yvs[r * 8 + b] = yv;
+                    if (j0 + b < n) (r == 0 ? yb : y1)[j0 + b] = yv;
+                } else if (lane < 24) {
+                    if (j0 + b < n) inv_c[j0 + b] = invs[b];
                 }
-            } else if (lane >= 8 && lane < 16) {
-                if (j0 + lane - 8 < n) inv_c[j0 + lane - 8] = invs[lane - 8];
             }
-            asm volatile("cp.async.wait_group 0;\n" ::);
         } else {
             // every window row against the factor: L (to HBM) and the panel P
 #pragma unroll 1
@@ -382,14 +490,26 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                     const int blo = dt - w, bhi = min(dt, n - 1 - j0);   // 0 <= e <= w and j0 + b < n  <=>  blo <= b <= bhi
 #pragma unroll
                     for (int b = 0; b < 8; b++)
+#ifndef ICARW_NOLSTORE
                         if (b >= blo && b <= bhi) lp[b * (W1 - 1)] = x[b];
+#else
+                        if (b >= blo && b <= bhi && x[b] == 1.2345e300) lp[b * (W1 - 1)] = x[b];
+#endif
                 }
 #pragma unroll
                 for (int b = 0; b < 8; b++) Ps[b * Wp + wrow] = pivot_row ? 0.0 : x[b];
             }
+            // the entering rows of this step (group m + NT) were requested one update phase ago by the last warp (which
+            // has the fewest window rows, none at all up to W = 64); they are consumed right after the barrier
+            if (warp == 3) asm volatile("cp.async.wait_group 0;\n" ::);
         }
+        ICARW_T(pt1);
         __syncthreads();   // panel, y and the staged entering rows are visible
         // ===== update phase =====
+        ICARW_T(pt2);
+#ifdef ICARW_PROF
+        long long ps0 = 0, ps1 = 0, ps2 = 0, ps3 = 0;
+#endif
         if (warp == 0) {
             // look-ahead: the next pivot block gets its rank-8 update first and is factorised right away, while the
             // other warps update the rest of the window
@@ -403,10 +523,64 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                 dgemm::dmma884(cv.x, cv.y, a1, b1);
                 *cp = cv;
                 __syncwarp();
+                ICARW_T(pc0);
                 if (!icarw_chol8(Dn, Lds, invs, lane)) piv_ok = 0;
+                ICARW_T(pc1);
+                ICARW_ACC(pr_chol, pc1, pc0);
             }
         } else {
             const int hw = warp - 1;   // 0..2
+            // the pivot slot leaves -- the row phase was the last reader of its tiles -- and takes the 8 entering rows
+            // (group m + NT) FIRST, so that the staging buffer is free again for the rest of the phase
+            ICARW_SET(ps0);
+            if (NT_T > 0) {
+                // the slot at distance r from the pivot slot holds group m + r, D = 8 (NT - r) matrix rows above the
+                // entering group: Lambda[hi][lo] = tau Q[hi][hi - lo] with hi always in the entering (staged) group, so a
+                // tile differs from the next only by D -- the lane's two offsets into the staged rows are loop constants
+                for (int r = 1 + hw; r < NT; r += 3) {
+                    const int a = cs + r >= NT ? cs + r - NT : cs + r;
+                    const int D = 8 * (NT - r);
+                    double v0, v1;
+                    double* tile;
+                    if (a > cs) {   // tile (a, cs): the columns are the entering group
+                        const double* row = stg + rf_cols + D;
+                        v0 = tau * row[0];
+                        v1 = tau * row[W1p + 1];
+                        tile = Ts + (a * (a + 1) / 2 + cs) * 64;
+                    } else {        // tile (cs, a): the rows are the entering group
+                        const double* row = stg + rf_rows + D;
+                        v0 = tau * row[0];
+                        v1 = tau * row[-1];
+                        tile = Ts + (cs * (cs + 1) / 2 + a) * 64;
+                    }
+                    *reinterpret_cast<double2*>(tile + g * 8 + 2 * t4) = make_double2(v0, v1);
+                }
+                if (hw == 1) fill_tile_diag(stg, 8 * (m + NT), cs);
+                if (hw == 0) fill_rhs(stg, cs, 8 * (m + NT));
+            } else {
+                const int rn = 8 * (m + NT);
+                for (int a = hw; a < NT; a += 3) {
+                    if (a == cs) {
+                        fill_tile_diag(stg, rn, cs);
+                    } else {
+                        const int grp = m + (a >= cs ? a - cs : a - cs + NT);
+                        if (a > cs) fill_tile_off(stg, rn, a, cs, 8 * grp, rn);
+                        else fill_tile_off(stg, rn, cs, a, rn, 8 * grp);
+                    }
+                }
+                if (hw == 0) fill_rhs(stg, cs, rn);
+            }
+            ICARW_SET(ps1);
+            asm volatile("bar.sync 1, 96;\n" ::: "memory");   // warps 1..3: everybody has read the staged group
+            ICARW_SET(ps2);
+            // the rows of the NEXT step travel (L2 / HBM latency: ~3000 cycles when exposed) while the window is updated
+#ifndef ICARW_NOSTAGE   // (measurement builds: -DICARW_NOSTAGE / -DICARW_NOLSTORE drop a piece to time the rest; wrong results)
+            if (warp == 3 && m + 1 < nsteps) {
+                const int nb = 8 * (m + 1 + NT);
+                if ((W1 & 1) == 0 && nb >= w) stage_rows_fast(nb);
+                else stage_rows(nb, 0, 1);
+            }
+#endif
             // forward residuals of the rows that stay: rhs_r[row] -= y_r . P[row]
 #pragma unroll 1
             for (int wrow = tid - 32; wrow < W; wrow += T - 32) {
@@ -422,39 +596,13 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                     rhs[W + wrow] = r1;
                 }
             }
+            ICARW_SET(ps3);
             // rank-8 trailing update on the tensor pipe: tile (a, b) -= P_a P_b' for the slots that stay, dealt round-robin
             // to the three warps; the pivot slot's tiles are being refilled and the next pivot block belongs to warp 0
             if (NT_T > 0) {
-                // this warp's tiles of the step as a bit mask over the NT (NT + 1) / 2 stored pairs (<= 36): every third
-                // tile, without the pivot slot's row and column and without the next pivot block
-                unsigned long long mine = 0ull;
-                {
-                    constexpr int NTILES = (NT_T > 0 ? NT_T : 1) * ((NT_T > 0 ? NT_T : 1) + 1) / 2;
-                    unsigned long long third = 0ull;
-#pragma unroll
-                    for (int t = 0; t < NTILES; t++)
-                        if (t % 3 == 0) third |= 1ull << t;
-                    mine = third << hw;                               // tiles t = hw (mod 3)
-                    unsigned long long dead = 1ull << tri(cs1, cs1);
-                    for (int b = 0; b <= cs; b++) dead |= 1ull << tri(cs, b);        // row of the pivot slot
-                    for (int a = cs + 1; a < NT; a++) dead |= 1ull << tri(a, cs);    // its column
-                    mine &= ~dead & ((1ull << NTILES) - 1ull);
-                }
-#pragma unroll
-                for (int a = 0; a < (NT_T > 0 ? NT_T : 1); a++) {
-                    const double a0 = -Ps[t4 * Wp + 8 * a + g], a1 = -Ps[(4 + t4) * Wp + 8 * a + g];
-#pragma unroll
-                    for (int b = 0; b <= a; b++) {
-                        if ((mine >> (a * (a + 1) / 2 + b)) & 1ull) {
-                            const double b0 = Ps[t4 * Wp + 8 * b + g], b1 = Ps[(4 + t4) * Wp + 8 * b + g];
-                            double2* cp = reinterpret_cast<double2*>(Ts + (a * (a + 1) / 2 + b) * 64 + g * 8 + 2 * t4);
-                            double2 cv = *cp;
-                            dgemm::dmma884(cv.x, cv.y, a0, b0);
-                            dgemm::dmma884(cv.x, cv.y, a1, b1);
-                            *cp = cv;
-                        }
-                    }
-                }
+                if (hw == 0) icarw_update_tiles<NT_T, 0>(Ts, Ps, Wp, cs, g, t4);
+                else if (hw == 1) icarw_update_tiles<NT_T, 1>(Ts, Ps, Wp, cs, g, t4);
+                else icarw_update_tiles<NT_T, 2>(Ts, Ps, Wp, cs, g, t4);
             } else {
                 int tix = 0;
                 for (int a = 0; a < NT; a++) {
@@ -470,21 +618,24 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                     }
                 }
             }
-            // the pivot slot leaves; it takes the 8 entering rows (group m + NT)
-            const int rn = 8 * (m + NT);
-            for (int a = hw; a < NT; a += 3) {
-                if (a == cs) {
-                    fill_tile_diag(stg, rn, cs);
-                } else {
-                    const int grp = m + (a >= cs ? a - cs : a - cs + NT);
-                    if (a > cs) fill_tile_off(stg, rn, a, cs, 8 * grp, rn);
-                    else fill_tile_off(stg, rn, cs, a, rn, 8 * grp);
-                }
-            }
-            if (hw == 0) fill_rhs(stg, cs, rn);
         }
+#ifdef ICARW_PROF
+        if (warp != 0) {
+            const long long ps4 = clock64();
+            pr_refill += ps1 - ps0; pr_nb += ps2 - ps1; pr_resid += ps3 - ps2; pr_dmma += ps4 - ps3;
+        }
+#endif
+        ICARW_T(pt3);
         __syncthreads();   // window updated and refilled; next factor ready; staged group consumed
+        ICARW_T(pt4);
+        ICARW_ACC(pr_row, pt1, pt0);
+        ICARW_ACC(pr_b1, pt2, pt1);
+        ICARW_ACC(pr_upd, pt3, pt2);
+        ICARW_ACC(pr_b2, pt4, pt3);
     }
+#ifdef ICARW_PROF
+    const long long pr_t_fwd1 = clock64();
+#endif
     if (!piv_ok) {
         if (tid == 0) {
             v.status[c] = 1;
@@ -511,14 +662,25 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
         auto stage_block = [&](int j0, int buf) {
             double* dst = stgB + buf * stg_sz;
             if (j0 >= 0) {
+                if ((W1 & 1) == 0) {
+                    // 16-byte pieces, eight lanes per column: warps 0 and 1 take four columns each
+                    if (warp < 2) {
+                        const int bb = 4 * warp + (lane >> 3), e0 = 2 * (lane & 7);
+                        const bool okk = j0 + bb < n;
+                        const double* scol = Lc + (size_t)(okk ? j0 + bb : 0) * W1 + e0;
+                        double* d = dst + bb * W1p + e0;
+                        for (int e = e0; e < W1; e += 16, d += 16, scol += 16) icarw_cp16(d, scol, okk);
+                    }
+                } else {
 #pragma unroll 1
-                for (int bb = warp; bb < 8; bb += 4) {
-                    const bool okk = j0 + bb < n;
-                    const double* scol = Lc + (size_t)(okk ? j0 + bb : 0) * W1;
-                    for (int e = lane; e < W1; e += 32) icarw_cp8(dst + bb * W1p + e, scol + e, okk);
+                    for (int bb = warp; bb < 8; bb += 4) {
+                        const bool okk = j0 + bb < n;
+                        const double* scol = Lc + (size_t)(okk ? j0 + bb : 0) * W1;
+                        icarw_stage_line(dst + bb * W1p, scol, W1, okk, lane);
+                    }
                 }
-                if (tid < 32) {
-                    const int which = tid >> 3, bb = tid & 7, j = j0 + bb;
+                if (warp == 2) {
+                    const int which = lane >> 3, bb = lane & 7, j = j0 + bb;
                     const double* srcv = which == 0 ? yb : (which == 1 ? y1 : (which == 2 ? zs : inv_c));
                     icarw_cp8(dst + 8 * W1p + which * 8 + bb, j < n ? srcv + j : srcv, j < n);
                 }
@@ -552,24 +714,27 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                 Ss[warp * 32 + g * 4 + 2 * t4 + 1] = s1;
             }
             __syncthreads();
-            if (tid < 3) {  // one lane per right-hand side finishes the 8 x 8 triangular solve
-                const int r = tid;
-                double xb8[8];
+            if (warp == 0) {
+                // the 8 x 8 triangular solves L_JJ' x = t of the three right-hand sides: lane 8 r + b holds entry b of
+                // right-hand side r; from the last column up, the solved entry is broadcast by a shuffle and eliminated
+                // from the entries above it (8 dependent steps; one lane per right-hand side needed 36)
+                const int b = lane & 7, r = lane >> 3;   // r = 3: idle copy of r = 2's arithmetic, never stored
+                const int rr = r < 3 ? r : 2;
+                const double ybv = sb[8 * W1p + b];
+                double t = (rr == 0 ? ybv + sb[8 * W1p + 16 + b] : (rr == 1 ? sb[8 * W1p + 8 + b] : ybv)) -
+                           ((Ss[b * 4 + rr] + Ss[32 + b * 4 + rr]) + (Ss[64 + b * 4 + rr] + Ss[96 + b * 4 + rr]));
+                const double ib = sb[8 * W1p + 24 + b];   // 1 / L_jj, staged as zero for the padded columns j >= n
+                double xv = 0.0;
 #pragma unroll
-                for (int b = 7; b >= 0; b--) {
-                    const double ybv = sb[8 * W1p + b];
-                    double t = (r == 0 ? ybv + sb[8 * W1p + 16 + b] : (r == 1 ? sb[8 * W1p + 8 + b] : ybv)) -
-                               ((Ss[b * 4 + r] + Ss[32 + b * 4 + r]) + (Ss[64 + b * 4 + r] + Ss[96 + b * 4 + r]));
-#pragma unroll
-                    for (int bb = b + 1; bb < 8; bb++) t = fma(-sb[b * W1p + (bb - b)], xb8[bb], t);
-                    xb8[b] = t * sb[8 * W1p + 24 + b];   // 1 / L_jj, staged as zero for the padded columns j >= n
+                for (int j = 7; j >= 0; j--) {
+                    const double xj = __shfl_sync(0xffffffffu, t * ib, (lane & 24) | j);
+                    if (b == j) xv = xj;
+                    if (b < j) t = fma(-sb[b * W1p + (j - b)], xj, t);
                 }
-                double* dst = r == 0 ? xs : (r == 1 ? zs : ms);
-                const int slot = j0 % W;
-#pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    xr[r * W + slot + b] = xb8[b];       // blocks are 8-aligned: no wrap inside a block
-                    if (j0 + b < n) dst[j0 + b] = xb8[b];
+                if (r < 3) {
+                    double* dst = r == 0 ? xs : (r == 1 ? zs : ms);
+                    xr[r * W + (j0 % W) + b] = xv;       // blocks are 8-aligned: no wrap inside a block
+                    if (j0 + b < n) dst[j0 + b] = xv;
                 }
             }
             ring0 -= 8;
@@ -580,6 +745,11 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     }
     __threadfence_block();
     __syncthreads();
+#ifdef ICARW_PROF
+    if ((c == 0 || c == 500) && lane == 0 && v.ctl->iter == 3)
+        printf("icarw chain %d warp %d: steps %d  forward %lld cyc (row %lld, barrier %lld, update %lld [chol8 %lld | refill %lld, named barrier %lld, residuals %lld, dmma %lld], barrier %lld)  backward %lld cyc\n",
+               c, warp, nsteps, pr_t_fwd1 - pr_t_fwd0, pr_row, pr_b1, pr_upd, pr_chol, pr_refill, pr_nb, pr_resid, pr_dmma, pr_b2, clock64() - pr_t_fwd1);
+#endif
 
     // ---- eta = x - (sum x / sum zv) zv (distributions.pyx:24-39); beta system (logit.py:226-231) ----
     double sx = 0.0, sz = 0.0;
