@@ -53,14 +53,19 @@ __host__ __device__ inline int icarw_nt(int bw) {
     const int need = icarw_nt_needed(bw);
     return need <= 8 ? (need + 1) / 2 * 2 : need;
 }
-__host__ __device__ inline int icarw_wp(int nt) { return (nt & 1) ? 8 * nt : 8 * nt + 8; }   // panel pitch = 8 mod 16 doubles
+// panel pitch = 4 mod 16 doubles: the DMMA fragment loads Ps[t4 * Wp + 8 slot + g] of a half warp (g = 0..3, t4 = 0..3)
+// then touch 16 distinct bank pairs (with 8 mod 16 the rows t4 and t4 + 2 collided: 4 wavefronts per load instead of 2,
+// and the shared-memory pipe is what seven resident chains per SM saturate)
+__host__ __device__ inline int icarw_wp(int nt) { return (nt & 1) ? 8 * nt + 12 : 8 * nt + 4; }
+// pitch of the backward pass's ring of solved right-hand sides, same rule (B fragments xr[g * Wx + ring])
+__host__ __device__ inline int icarw_wx(int nt) { return 8 * nt + 4; }
 // staged band rows: W + 8 doubles, zero beyond the band, so that both passes read them without bounds checks (forward:
 // offsets up to W - 1; backward: up to bw + 10 <= W + 2)
 __host__ __device__ inline int icarw_pw(int nt) { return 8 * nt + 8; }
 // shared-memory layout (doubles): region A = window tiles (forward) / x ring + block sums + two staged factor blocks
 // (backward) | panel | forward residuals | one staged group of entering rows | beta system
 __host__ __device__ inline size_t icarw_region_a(int nt, int bw) {
-    const size_t tiles = (size_t)nt * (nt + 1) / 2 * 64, back = 8 * 8 * (size_t)nt + 128 + 2 * (8 * (size_t)icarw_pw(nt) + 32);
+    const size_t tiles = (size_t)nt * (nt + 1) / 2 * 64, back = 8 * (size_t)icarw_wx(nt) + 128 + 2 * (8 * (size_t)icarw_pw(nt) + 32);
     return tiles > back ? tiles : back;
 }
 static size_t icarw_smem_bytes(int bw, int p) {
@@ -143,7 +148,7 @@ __device__ __forceinline__ bool icarw_chol8(const double* __restrict__ D, double
     const int a = lane & 7;
     double row[8];
 #pragma unroll
-    for (int b = 0; b < 8; b++) row[b] = D[a * 8 + b];
+    for (int b = 0; b < 8; b++) row[b] = lane < 8 ? D[a * 8 + b] : 1.0;   // lanes 8..31 only take part in the shuffles
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -219,8 +224,9 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     const HParams* hp = v.hp;
     const int stg_sz = 8 * W1p + 32;              // 8 staged band rows + 4 x 8 scalars
     double* Ts = icw_sm;                          // [NT (NT + 1) / 2][8][8]  window tiles, pair (a, b), a >= b   (forward)
-    double* xr = icw_sm;                          // [8][W]   backward: ring of solved x, zv, m by (matrix row mod W); rows 3..7 zero
-    double* Ss = xr + 8 * W;                      // [4][8][4]  backward: block sums, one set per warp
+    const int Wx = icarw_wx(NT);
+    double* xr = icw_sm;                          // [8][Wx]  backward: ring of solved x, zv, m by (matrix row mod W); rows 3..7 zero
+    double* Ss = xr + 8 * Wx;                     // [4][8][4]  backward: block sums, one set per warp
     double* stgB = Ss + 128;                      // [2][stg_sz]  backward: staged factor blocks
     double* Ps = icw_sm + icarw_region_a(NT, w);  // [8][Wp]  panel, column-major: Ps[col][window row]
     double* rhs = Ps + 8 * Wp;                    // [2][W]   forward residuals of b and 1, by window row
@@ -653,7 +659,7 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
 
     // ---- blocked backward: L' x = y_b + eps, L' zv = y_1, L' m = y_b (its arrays take over the window's memory) ----
     __syncthreads();
-    for (int e = tid; e < 8 * W + 128 + 2 * stg_sz; e += T) xr[e] = 0.0;   // ring, sums, staging pads
+    for (int e = tid; e < 8 * Wx + 128 + 2 * stg_sz; e += T) xr[e] = 0.0;   // ring, sums, staging pads
     __syncthreads();
     {
         // the 8 column bands of a block are one contiguous piece of the factor: staged one block ahead (cp.async, two
@@ -701,7 +707,7 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
             // warp w takes the k steps w, w + 4, ...
             double s0 = 0.0, s1 = 0.0;
             const double* lcol = sb + g * W1p + (8 + t4 - g) + 4 * warp;   // entry e = 8 + 4 ks + t4 - g of column j0 + g
-            const double* xg = xr + g * W;
+            const double* xg = xr + g * Wx;
             int ring = ring0;
             for (int ks = warp; ks < ksteps; ks += 4) {
                 dgemm::dmma884(s0, s1, lcol[4 * (ks - warp)], xg[ring]);
@@ -733,7 +739,7 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
                 }
                 if (r < 3) {
                     double* dst = r == 0 ? xs : (r == 1 ? zs : ms);
-                    xr[r * W + (j0 % W) + b] = xv;       // blocks are 8-aligned: no wrap inside a block
+                    xr[r * Wx + (j0 % W) + b] = xv;      // blocks are 8-aligned: no wrap inside a block
                     if (j0 + b < n) dst[j0 + b] = xv;
                 }
             }
