@@ -172,12 +172,13 @@ __device__ __forceinline__ bool icarw_chol8(const double* __restrict__ D, double
     return ok;
 }
 
-// Rank-8 trailing update of one of the three update warps (HW = 0..2) for a compiled window size: the tiles that stay,
-// named by their slot distances (ra, rb) from the pivot slot, 1 <= rb <= ra <= NT - 1 without (1, 1) (the next pivot
-// block, which warp 0 updates and factorises), are numbered row by row and dealt 3 : 3 : 4 to the warps -- the last warp
-// has no window rows to solve up to W = 64.  The list is a compile-time constant, so a warp executes exactly its own
-// tiles: a lone warp issues an instruction every ~6 cycles, and the earlier version, which walked all NT (NT + 1) / 2
-// stored pairs under predicates, spent 342 issue slots per step on the critical path of the factorisation.
+// Rank-8 trailing update of one of the three update warps (HW = 0..2) for a compiled window size.  The tiles that stay
+// are named by their slot distances (ra, rb) from the pivot slot, 1 <= rb <= ra <= NT - 1, without (1, 1) (the next
+// pivot block, which warp 0 updates and factorises).  Whole ROWS ra are dealt to the warps, from the longest down in the
+// order 2 0 1 2 1 0 (NT = 8: 11 / 8 / 8 tiles; the last warp has no window rows to solve up to W = 64), so a warp reads
+// the panel fragment of its row once and executes exactly its own tiles -- the list is a compile-time constant.  (A lone
+// warp issues an instruction every ~6 cycles: the earlier version, which walked all NT (NT + 1) / 2 stored pairs under
+// predicates, spent 342 issue slots per step on the critical path of the factorisation.)
 // tile (hi, lo) -= P_hi P_lo' with hi / lo the larger / smaller SLOT of the pair (only slot pairs a >= b are stored);
 // the A and B fragments of a slot are the same two panel entries, the minus sign is an operand modifier of the DMMA.
 template <int NT, int HW>
@@ -191,19 +192,27 @@ __device__ __forceinline__ void icarw_update_tiles(double* __restrict__ Ts, cons
     }
     const double* p0 = Ps + t4 * Wp + g;
     const double* p1 = Ps + (4 + t4) * Wp + g;
-    int k = 0;
 #pragma unroll
-    for (int ra = 2; ra < NT; ra++) {
+    for (int ra = NT - 1; ra >= 2; ra--) {
+        const int k = (NT - 1 - ra) % 6;
+        const int owner = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 1 : (k == 3 ? 2 : (k == 4 ? 1 : 0))));
+        if (owner != HW) continue;
+        const int sa = slot[ra];
+        const double fa0 = p0[8 * sa], fa1 = p1[8 * sa];
 #pragma unroll
-        for (int rb = 1; rb <= ra; rb++, k++) {
-            const int owner = (k % 10) < 4 ? 2 : ((k % 10) < 7 ? 0 : 1);
-            if (owner != HW) continue;
-            const int hi = max(slot[ra], slot[rb]), lo = min(slot[ra], slot[rb]);
-            const double a0 = p0[8 * hi], a1 = p1[8 * hi], b0 = p0[8 * lo], b1 = p1[8 * lo];
+        for (int rb = 1; rb <= ra; rb++) {
+            const int sb = slot[rb];
+            const double fb0 = p0[8 * sb], fb1 = p1[8 * sb];
+            const int hi = max(sa, sb), lo = min(sa, sb);
             double2* cp = reinterpret_cast<double2*>(Ts + (hi * (hi + 1) / 2 + lo) * 64 + g * 8 + 2 * t4);
             double2 cv = *cp;
-            dgemm::dmma884(cv.x, cv.y, -a0, b0);
-            dgemm::dmma884(cv.x, cv.y, -a1, b1);
+            if (sa >= sb) {   // uniform: the row slot is the tile's row side
+                dgemm::dmma884(cv.x, cv.y, -fa0, fb0);
+                dgemm::dmma884(cv.x, cv.y, -fa1, fb1);
+            } else {
+                dgemm::dmma884(cv.x, cv.y, -fb0, fa0);
+                dgemm::dmma884(cv.x, cv.y, -fb1, fa1);
+            }
             *cp = cv;
         }
     }
