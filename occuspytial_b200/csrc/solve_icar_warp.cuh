@@ -12,15 +12,18 @@
 // (ensure_sums_to_zero, distributions.pyx:24-39).
 //
 // Mapping.  FOUR WARPS own a chain (a 128-thread CTA at <= 72 registers, so that 7 CTAs -- the 1024 chains of BASELINE
-// config 4 in one wave -- stay resident per SM), each with its own job, two barriers per block step:
+// config 4 in one wave -- stay resident per SM), each with its own job, two CTA barriers per block step:
 //   warp 0      the serial part: the 8 x 8 pivot block of the NEXT block step -- its rank-8 update, then its Cholesky
 //               factorisation, lanes 0..7 holding one row each and exchanging columns by shuffles (8 dependent rsqrt:
 //               the irreducible chain) -- runs while the other warps do the trailing update of the CURRENT step
-//               (look-ahead); during the row phase it stages the next entering rows (cp.async) and solves the two
-//               right-hand sides;
+//               (look-ahead); during the row phase it solves the two right-hand sides (eight lanes each, shuffles);
 //   warps 1..3  row phase: every thread solves one window row against the factor (read as shared-memory broadcasts),
-//               writes that row of L to HBM (column-band layout) and into the panel P; update phase: forward residuals,
-//               rank-8 DMMA update of the tiles that stay (dealt round-robin), refill of the leaving slot.
+//               writes that row of L to HBM (column-band layout) and into the panel P; update phase: refill of the
+//               leaving slot from the staged rows, then -- after a named barrier of these three warps -- the last warp
+//               requests the rows that enter in the NEXT step (cp.async, consumed a whole phase later), forward
+//               residuals, rank-8 DMMA update of the tiles that stay (compile-time list per warp, dealt by window row).
+// A lone warp issues an instruction every ~6 cycles, so the instruction count of whichever warp the others wait for IS
+// the critical path (-DICARW_PROF prints cycle counts per phase and warp; DESIGN.md section 4 has the history).
 // One warp per chain (7 warps per SM) was bound by one chain's dependency latency at 25 % issue utilisation
 // (profiles/r02_ncu_icar_warp_v3.txt); two warps with a redundant pivot factorisation gained nothing.
 // The factorisation is right-looking in blocks of 8 columns over a sliding window of W = 8 NT >= bw + 8 matrix rows, kept
