@@ -47,27 +47,30 @@ __device__ bool block_cholesky_packed(double* A, int o, int d, int tid, int nthr
 // Sequential small dense solve by one thread: x = P^-1 b + L^-T z, P = L L' (full d x d row-major in S,
 // lower triangle overwritten by L).  Returns false on a non-positive pivot.  distributions.pyx:88-105.
 __device__ bool small_precision_mvnorm(double* S, int d, const double* b, const double* zn, double* x, double* tmp) {
+    // one rsqrt per pivot and multiplications by the reciprocal pivot instead of a square root and 2 d divisions (each
+    // a few dozen dependent FP64 instructions in a thread that a whole CTA may be waiting for); the diagonal of S
+    // receives 1 / L_jj
     for (int j = 0; j < d; j++) {
         double s = S[j * d + j];
         for (int k = 0; k < j; k++) s -= S[j * d + k] * S[j * d + k];
         if (!(s > 0.0)) return false;
-        const double dj = sqrt(s);
-        S[j * d + j] = dj;
+        const double inv = rsqrt(s);
+        S[j * d + j] = inv;
         for (int i = j + 1; i < d; i++) {
             double t = S[i * d + j];
             for (int k = 0; k < j; k++) t -= S[i * d + k] * S[j * d + k];
-            S[i * d + j] = t / dj;
+            S[i * d + j] = t * inv;
         }
     }
     for (int i = 0; i < d; i++) {  // L y = b
         double t = b[i];
         for (int k = 0; k < i; k++) t -= S[i * d + k] * tmp[k];
-        tmp[i] = t / S[i * d + i];
+        tmp[i] = t * S[i * d + i];
     }
     for (int i = d - 1; i >= 0; i--) {  // L' x = y + z
         double t = tmp[i] + zn[i];
         for (int k = i + 1; k < d; k++) t -= S[k * d + i] * x[k];
-        x[i] = t / S[i * d + i];
+        x[i] = t * S[i * d + i];
     }
     return true;
 }
@@ -185,6 +188,12 @@ __device__ __forceinline__ bool chol4(double (&a)[4][4], double (&invd)[4]) {
 __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const View v, const SolveDebug dbg,
                                                                          double* rec_alpha, double* rec_beta,
                                                                          double* rec_tau, int rec_capacity) {
+#ifdef RSRS_PROF   // measurement builds: cycles per phase of chain 0, thread 0
+#define RSRS_MARK(k) do { if (tid == 0) { const long long t_ = clock64(); rs_t[k] += t_ - rs_last; rs_last = t_; } } while (0)
+    long long rs_t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, rs_last = clock64();
+#else
+#define RSRS_MARK(k)
+#endif
     extern __shared__ double sm_dyn[];
     const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;  // 64 (q <= 128) or SOLVE_THREADS
     double* sm = v.solve_stride ? v.solve_scratch + (size_t)c * v.solve_stride : sm_dyn;
@@ -253,13 +262,33 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
     if (tid == 0) ok_flag = 1;
     __syncthreads();
 
+    RSRS_MARK(0);
     // ---- tau | eta   (logit.py:206-209) ----
     {
         double part = 0.0;
-#pragma unroll 8
-        for (int idx = tid; idx < q * q; idx += T) {
-            const int i = idx / q, j = idx - i * q;
-            part += th[p + i] * v.Qrsr[idx] * th[p + j];
+        // one warp per row of Qrsr, lanes along the row (coalesced; no division to decode a flat index), eight rows in
+        // flight per warp: all loads of a batch are issued before any is consumed
+        const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
+        const double t0 = lane < q ? th[p + lane] : 0.0, t1 = lane + 32 < q ? th[p + lane + 32] : 0.0;
+        for (int i0 = warp; i0 < q; i0 += 8 * nwarp) {
+            double qv[8][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * nwarp;
+                const double* qrow = v.Qrsr + (size_t)(i < q ? i : 0) * q;
+                qv[u][0] = (i < q && lane < q) ? qrow[lane] : 0.0;
+                qv[u][1] = (i < q && lane + 32 < q) ? qrow[lane + 32] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * nwarp;
+                if (i < q) part += th[p + i] * (qv[u][0] * t0 + qv[u][1] * t1);
+            }
+            for (int i = i0; i < q && i < i0 + 8 * nwarp; i += nwarp) {   // columns beyond 64 (q > 64)
+                double rowsum = 0.0;
+                for (int j = 64 + lane; j < q; j += 32) rowsum += v.Qrsr[(size_t)i * q + j] * th[p + j];
+                part += th[p + i] * rowsum;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -277,6 +306,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
     }
     const double tau = red[T / 32];
 
+    RSRS_MARK(1);
     // ---- stage the joint Gram: XX block, KX rows, and Lambda = K' Om K + tau Qrsr in blocked form ----
     for (int idx = tid; idx < nblk * BLK; idx += T) Bs[idx] = 0.0;
     for (int idx = tid; idx < p * p; idx += T) {
@@ -336,6 +366,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
             dbg.out.eta_prec[(size_t)c * q * q + idx] = Bs[bidx(ii >> 2, jj >> 2) + (ii & 3) * 4 + (jj & 3)];
         }
 
+    RSRS_MARK(2);
     // ---- blocked right-looking Cholesky of the augmented matrix ----
     for (int J = 0; J < qb; J++) {
         // (1) panel: blocks (I, J), I = J .. qb
@@ -375,6 +406,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
                 }
             }
         }
+        RSRS_MARK(3);
         __syncthreads();
         if (!ok_flag) break;
         // (2) trailing update: blocks (J+1+ii, J+1+kk), kk <= ii <= qb-J-1
@@ -397,7 +429,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
                     A[a * 4 + b] -= p0 * pk[b][0] + p1 * pk[b][1] + p2 * pk[b][2] + p3 * pk[b][3];
             }
         }
+        RSRS_MARK(4);
         __syncthreads();
+        RSRS_MARK(5);
     }
     if (!ok_flag) {
         if (tid == 0) {
@@ -413,6 +447,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
             dbg.out.eta_chol[(size_t)c * q * q + idx] = (j <= i) ? (I == K ? Ld[I * 16 + e] : Bs[bidx(I, K) + e]) : 0.0;
         }
 
+    RSRS_MARK(6);
     // ---- backward, right-looking over block rows: L' m = y (mean) and L' e = eps ----
     // thread J owns the two 4-vectors of block row J
     double rm[4] = {0, 0, 0, 0}, re[4] = {0, 0, 0, 0};
@@ -463,12 +498,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
     for (int i = tid; i < q; i += T) th[p + i] = xm[i] + xe[i];  // eta = mean + L^-T eps
     __syncthreads();
 
+    RSRS_MARK(7);
     // ---- beta | .   A = X' Om X + b_prec,  b = X'k - (X' Om K) eta + b_prec b_mu   (logit.py:226-232) ----
     for (int idx = tid; idx < p * p; idx += T) small_S[idx] = gxx[idx] + hp->b_prec[idx];
-    for (int a = tid; a < p; a += T) {
-        double b = h[a] + hp->b_pm[a];
-        for (int j = 0; j < q; j++) b -= gx[j * p + a] * th[p + j];
-        small_b[a] = b;
+    for (int a = tid >> 5; a < p; a += T >> 5) {   // one warp per component: lanes along eta, fixed-order reduction
+        double acc = 0.0;
+        for (int j = tid & 31; j < q; j += 32) acc += gx[j * p + a] * th[p + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) small_b[a] = h[a] + hp->b_pm[a] - acc;
     }
     __syncthreads();
     if (dbg.enabled && c < v.C) {
@@ -495,6 +533,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
         return;
     }
 
+    RSRS_MARK(8);
     // ---- commit state, record the draw (Chain.append, chain.py:56-74) ----
     for (int a = tid; a < pq; a += T) v.theta[(size_t)a * Cp + c] = th[a];
     if (tid == 0) v.tau[c] = tau;
@@ -503,4 +542,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 6) solve_logit_rsr_kernel(const
         for (int a = tid; a < p; a += T) rec_beta[row * p + a] = th[a];
         if (tid == 0) rec_tau[row] = tau;
     }
+#ifdef RSRS_PROF
+    RSRS_MARK(9);
+    if (c == 0 && tid == 0 && v.ctl->iter == 3)
+        printf("rsr solve chain 0 (thread 0): prologue %lld | tau %lld | stage-in %lld | chol: panel %lld, barrier + update %lld, "
+               "barrier %lld | post %lld | backward %lld | beta %lld | commit %lld cycles\n",
+               rs_t[0], rs_t[1], rs_t[2], rs_t[3], rs_t[4], rs_t[5], rs_t[6], rs_t[7], rs_t[8], rs_t[9]);
+#endif
 }
