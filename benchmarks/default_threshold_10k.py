@@ -2,10 +2,11 @@
 """LogitRSRGibbs with the reference's DEFAULT arguments (threshold r = 0.5 -> q ~ 0.126 n) at the headline size
 n = 10^4: constructor time (device eigh of the Moran operator), workspace, and per-kernel times of the sweep."""
 import json
+import os
 import sys
 import time
 
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from occuspytial_b200 import LogitRSRGibbs
@@ -18,7 +19,7 @@ s = LogitRSRGibbs(Q, W, X, y, random_state=10)      # r = 0.5, q = None: the ref
 ctor = time.perf_counter() - t0
 t0 = time.perf_counter()
 eng = s._make_engine(chains, seed=1)
-eng.set_start(s._start_to_engine(s._start_arrays(chains, None)))
+eng.draw_start(1, *s._DEFAULT_START)
 setup = time.perf_counter() - t0
 fails = eng.sweep(2)
 eng.set_profiling(True)

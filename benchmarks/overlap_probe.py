@@ -26,7 +26,7 @@ def main():
         engines = []
         for k in range(E):
             eng = sampler._make_engine(per, 12345, chain_offset=k * per, device='cuda:0', slot=k)
-            eng.set_start(sampler._start_arrays_range(12345, k * per, (k + 1) * per, None))
+            eng.draw_start(12345, *sampler._DEFAULT_START)
             engines.append(eng)
 
         def run(n):
