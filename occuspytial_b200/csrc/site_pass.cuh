@@ -442,11 +442,15 @@ __global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : (R <= 3 ? 6 : (R <= 5 ? 
     for (int k = 0; k < NV; k++) acc[k] = 0.0;
 
     if (FUSE_PSI) psi_tile_dmma(v, i0, tid, c, psi_s);
+    // eps of the next site is requested one site ahead: it comes from HBM (the array does not fit L2) and is needed at the
+    // very top of a site's work, where its latency would be exposed once per site
+    double ep_next = i0 < i1 ? v.eps[(size_t)i0 * Cp + c] : 0.0;
     for (int i = i0; i < i1; i++) {
         const int cls = v.site_class[i];
         const size_t off = (size_t)i * Cp + c;
         const double lp = FUSE_PSI ? (double)psi_s[i - i0][tid] : v.psi[off];   // x_i beta + K_i eta
-        const double ep = v.eps[off];
+        const double ep = ep_next;
+        if (i + 1 < i1) ep_next = v.eps[off + Cp];
         const double loc = lp + ep;
         const int v0 = v.visit_ptr[i], v1 = v.visit_ptr[i + 1];
         int zc;
