@@ -228,6 +228,10 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     extern __shared__ __align__(16) double icw_sm[];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = ICARW_THREADS;
     const int g = lane >> 2, t4 = lane & 3;
+#ifdef ICARW_PROF
+    const long long pr_t_start = clock64();
+    long long pr_t_tau = 0, pr_t_inputs = 0, pr_t_bwd_end = 0;
+#endif
     const int n = v.n, n4 = round_up_dev(v.n, 4), p = v.p, w = v.bw, W1 = v.bw + 1;
     const int NT = NT_T > 0 ? NT_T : icarw_nt(w), W = 8 * NT, Wp = icarw_wp(NT);
     const int W1p = icarw_pw(NT);
@@ -313,6 +317,9 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     const double tau = dbg.tau_in ? dbg.tau_in[cr] : v.gam[c] / rate;
     if (tid == 0 && dbg.enabled && dbg.out.tau_rate && c < v.C) dbg.out.tau_rate[c] = rate;
 
+#ifdef ICARW_PROF
+    pr_t_tau = clock64();
+#endif
     // ---- stage this chain's per-site inputs contiguously (the chain-minor state arrays would cost one uncoalesced
     //      access per row inside the sequential loops; the Box-Muller normals must not sit on the critical path) ----
     for (int i = tid; i < n4; i += T) {
@@ -339,6 +346,9 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     }
     __syncthreads();
 
+#ifdef ICARW_PROF
+    pr_t_inputs = clock64();
+#endif
     // ---- entering rows: the 8 band rows of Q, omega and b of the group starting at `base` -> the staging buffer
     //      (cp.async by the calling warp(s): `first`, `step` give the rows each warp takes) ----
     auto stage_rows = [&](int base, int first, int step) {
@@ -764,43 +774,110 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
     __threadfence_block();
     __syncthreads();
 #ifdef ICARW_PROF
+    pr_t_bwd_end = clock64();
+    if (c == 0 && tid == 0 && v.ctl->iter == 3)
+        printf("icarw chain 0: tau %lld | inputs + normals %lld | initial window %lld | forward %lld | backward %lld cycles\n",
+               pr_t_tau - pr_t_start, pr_t_inputs - pr_t_tau, pr_t_fwd0 - pr_t_inputs, pr_t_fwd1 - pr_t_fwd0, pr_t_bwd_end - pr_t_fwd1);
     if ((c == 0 || c == 500) && lane == 0 && v.ctl->iter == 3)
         printf("icarw chain %d warp %d: steps %d  forward %lld cyc (row %lld, barrier %lld, update %lld [chol8 %lld | refill %lld, named barrier %lld, residuals %lld, dmma %lld], barrier %lld)  backward %lld cyc\n",
                c, warp, nsteps, pr_t_fwd1 - pr_t_fwd0, pr_row, pr_b1, pr_upd, pr_chol, pr_refill, pr_nb, pr_resid, pr_dmma, pr_b2, clock64() - pr_t_fwd1);
 #endif
 
     // ---- eta = x - (sum x / sum zv) zv (distributions.pyx:24-39); beta system (logit.py:226-231) ----
-    double sx = 0.0, sz = 0.0;
-    for (int i = tid; i < n; i += T) {
-        sx += xs[i];
-        sz += zs[i];
-    }
-    sx = cta4_sum(sx, red);
-    sz = cta4_sum(sz, red + 4);
-    const double shift = -sx / sz;
-    for (int i = tid; i < n; i += T) {
-        const double e = xs[i] + shift * zs[i];
-        xs[i] = e;
-        v.eta_n[(size_t)i * Cp + c] = e;
-        if (dbg.enabled && dbg.out.eta_mean && c < v.C) dbg.out.eta_mean[(size_t)c * n + i] = ms[i];
-    }
-    __syncthreads();
-    for (int idx = 0; idx < p * p; idx++) {  // A = X' Om X + b_prec
-        const int a = idx / p, b = idx - a * p;
-        if (b > a) continue;
-        double sacc = 0.0;
-        for (int i = tid; i < n; i += T) sacc += om_c[i] * v.X[(size_t)i * p + a] * v.X[(size_t)i * p + b];
-        sacc = cta4_sum(sacc, red);
-        if (tid == 0) {
-            small_S[a * p + b] = sacc + hp->b_prec[a * p + b];
-            small_S[b * p + a] = sacc + hp->b_prec[b * p + a];
+    // ONE pass over the sites gathers every sum the rest needs -- sum x, sum zv, the p (p + 1) / 2 entries of X' Om X and,
+    // because eta = x + shift zv is linear in the not yet known shift, the two halves X'(k - Om x) and X' Om zv of the
+    // right-hand side -- and one fixed-order reduction combines them (eleven separate passes with two barriers each, every
+    // one a chain of dependent global loads, cost 0.3 M cycles per chain).  p <= 4 keeps the sums in registers; larger p
+    // falls back to a pass per sum.
+    double shift;
+    if (p <= 4) {
+        constexpr int PM = 4, NS = 2 + PM * (PM + 1) / 2 + 2 * PM;   // 20 sums
+        double acc[NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) acc[k] = 0.0;
+        for (int i = tid; i < n; i += T) {
+            const double xi = xs[i], zi = zs[i], om = om_c[i], kk = kd_c[i];
+            double xr_[PM];
+#pragma unroll
+            for (int a = 0; a < PM; a++) xr_[a] = a < p ? v.X[(size_t)i * p + a] : 0.0;
+            acc[0] += xi;
+            acc[1] += zi;
+            int k = 2;
+#pragma unroll
+            for (int a = 0; a < PM; a++)
+#pragma unroll
+                for (int bb = 0; bb <= a; bb++, k++) acc[k] += om * xr_[a] * xr_[bb];
+#pragma unroll
+            for (int a = 0; a < PM; a++) {
+                acc[k + a] += xr_[a] * (kk - om * xi);
+                acc[k + PM + a] += xr_[a] * (om * zi);
+            }
         }
-    }
-    for (int a = 0; a < p; a++) {  // b = X'(k - omega * eta) + b_prec b_mu
-        double sacc = 0.0;
-        for (int i = tid; i < n; i += T) sacc += v.X[(size_t)i * p + a] * (kd_c[i] - om_c[i] * xs[i]);
-        sacc = cta4_sum(sacc, red + 4);
-        if (tid == 0) small_b[a] = sacc + hp->b_pm[a];
+#pragma unroll
+        for (int k = 0; k < NS; k++) acc[k] = warp_sum(acc[k]);
+        double* redv = Ps;   // [4][NS]: the panel is free after the factorisation
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) redv[warp * NS + k] = acc[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NS; k++) acc[k] = (redv[k] + redv[NS + k]) + (redv[2 * NS + k] + redv[3 * NS + k]);
+        shift = -acc[0] / acc[1];
+        if (tid == 0) {
+            int k = 2;
+#pragma unroll
+            for (int a = 0; a < PM; a++)
+#pragma unroll
+                for (int bb = 0; bb <= a; bb++, k++)
+                    if (a < p) {
+                        small_S[a * p + bb] = acc[k] + hp->b_prec[a * p + bb];
+                        small_S[bb * p + a] = acc[k] + hp->b_prec[bb * p + a];
+                    }
+#pragma unroll
+            for (int a = 0; a < PM; a++)   // X'(k - Om eta) + b_prec b_mu
+                if (a < p) small_b[a] = (acc[k + a] - shift * acc[k + PM + a]) + hp->b_pm[a];
+        }
+        for (int i = tid; i < n; i += T) {
+            const double e = xs[i] + shift * zs[i];
+            xs[i] = e;
+            v.eta_n[(size_t)i * Cp + c] = e;
+            if (dbg.enabled && dbg.out.eta_mean && c < v.C) dbg.out.eta_mean[(size_t)c * n + i] = ms[i];
+        }
+    } else {
+        double sx = 0.0, sz = 0.0;
+        for (int i = tid; i < n; i += T) {
+            sx += xs[i];
+            sz += zs[i];
+        }
+        sx = cta4_sum(sx, red);
+        sz = cta4_sum(sz, red + 4);
+        shift = -sx / sz;
+        for (int i = tid; i < n; i += T) {
+            const double e = xs[i] + shift * zs[i];
+            xs[i] = e;
+            v.eta_n[(size_t)i * Cp + c] = e;
+            if (dbg.enabled && dbg.out.eta_mean && c < v.C) dbg.out.eta_mean[(size_t)c * n + i] = ms[i];
+        }
+        __syncthreads();
+        for (int idx = 0; idx < p * p; idx++) {  // A = X' Om X + b_prec
+            const int a = idx / p, b = idx - a * p;
+            if (b > a) continue;
+            double sacc = 0.0;
+            for (int i = tid; i < n; i += T) sacc += om_c[i] * v.X[(size_t)i * p + a] * v.X[(size_t)i * p + b];
+            sacc = cta4_sum(sacc, red);
+            if (tid == 0) {
+                small_S[a * p + b] = sacc + hp->b_prec[a * p + b];
+                small_S[b * p + a] = sacc + hp->b_prec[b * p + a];
+            }
+        }
+        for (int a = 0; a < p; a++) {  // b = X'(k - omega * eta) + b_prec b_mu
+            double sacc = 0.0;
+            for (int i = tid; i < n; i += T) sacc += v.X[(size_t)i * p + a] * (kd_c[i] - om_c[i] * xs[i]);
+            sacc = cta4_sum(sacc, red + 4);
+            if (tid == 0) small_b[a] = sacc + hp->b_pm[a];
+        }
     }
     __syncthreads();
     if (dbg.enabled && c < v.C) {
@@ -832,4 +909,7 @@ __global__ void __launch_bounds__(ICARW_THREADS, NT_T > 0 ? 7 : 1) solve_logit_i
         for (int a = tid; a < p; a += T) rec_beta[row * p + a] = beta_s[a];
         if (tid == 0) rec_tau[row] = tau;
     }
+#ifdef ICARW_PROF
+    if (c == 0 && tid == 0 && v.ctl->iter == 3) printf("icarw chain 0: epilogue (projection, beta system, commit) %lld cycles\n", clock64() - pr_t_bwd_end);
+#endif
 }
