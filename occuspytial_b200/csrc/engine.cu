@@ -215,6 +215,7 @@ static int launch_gram_gemm(occu_engine* e, cudaStream_t st) {
     a.M = v.Cp; a.N = v.model == OCCU_PROBIT_RSR ? 0 : v.M_pad; a.K = v.n_pad;  // probit: only U'd
     a.lda = v.Cp; a.ldb = v.ldz; a.ldo = v.M_pad;
     a.A2 = v.kd; a.Out2 = v.Hpart; a.N2 = v.ldh; a.col2 = v.M_pad; a.ldo2 = v.ldh; a.ksplit = v.ksplit;
+    a.n2_valid = v.pq;
     CUDA_OK(dgemm::launch(a, st));
     e->launches++;
     return 0;
