@@ -5,6 +5,7 @@ the problem arrays, the record buffers), host<->device copies, and the CUDA stre
 goes through the C ABI in ``_lib`` (include/occu_b200.h).
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -45,6 +46,28 @@ def _engine_stream(torch, device, slot):
     return st
 
 
+# Slots are handed out per device under a lock: two engines alive at the same time -- the per-device threads of one
+# sample() call, or sample() calls from different host threads -- never share a stream or a staging buffer.
+_SLOT_LOCK = threading.Lock()
+_BUSY_SLOTS = {}
+
+
+def _acquire_slot(device):
+    key = str(device)
+    with _SLOT_LOCK:
+        busy = _BUSY_SLOTS.setdefault(key, set())
+        slot = 0
+        while slot in busy:
+            slot += 1
+        busy.add(slot)
+    return slot
+
+
+def _release_slot(device, slot):
+    with _SLOT_LOCK:
+        _BUSY_SLOTS.get(str(device), set()).discard(slot)
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -67,7 +90,7 @@ class DeviceEngine:
     """
 
     def __init__(self, model, problem, chains, seed, chain_offset=0, device=None, debug=False, pg_fp64=False,
-                 gram_int8=False, workspace=None, slot=0):
+                 gram_int8=False, workspace=None, slot=None):
         import time as _time
         t_begin = _time.perf_counter()
         torch = _torch()
@@ -78,7 +101,7 @@ class DeviceEngine:
         self.chains = int(chains)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.slot = int(slot)
+        self.slot = None   # assigned below, once the device is known (``slot=`` is accepted for compatibility and ignored)
         X = np.ascontiguousarray(problem['X'], dtype=np.float64)
         self.n, self.p = X.shape
         W_rows = np.ascontiguousarray(problem['W_rows'], dtype=np.float64)
@@ -87,6 +110,7 @@ class DeviceEngine:
         self.eta_dim = self.q if self.q else self.n
         self.icar_bw = int(problem.get('icar_bw', 0))
         with torch.cuda.device(self.device):
+            self.slot = _acquire_slot(self.device)
             self.stream = _engine_stream(torch, self.device, self.slot)
             dev = {}
 
@@ -368,6 +392,9 @@ class DeviceEngine:
             self.handle = None
             ws = self.workspace if keep_workspace else None
             self.workspace = None
+        if getattr(self, 'slot', None) is not None:
+            _release_slot(self.device, self.slot)
+            self.slot = None
         return ws
 
     def __del__(self):

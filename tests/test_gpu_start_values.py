@@ -118,3 +118,19 @@ def test_sample_default_start_does_not_depend_on_devices_or_sharding():
     h2, _, _ = b._run_shard('cuda:0', 128, 256, seed, None, 12, 2, None, False, None, True)
     np.testing.assert_array_equal(pa['tau'], np.concatenate([h1['tau'], h2['tau']]))
     np.testing.assert_array_equal(pa['beta'], np.concatenate([h1['beta'], h2['beta']]))
+
+
+def test_concurrent_engines_do_not_share_stream_or_staging():
+    """Two engines alive at the same time on one device get different slots (stream, page-locked staging buffers); a
+    closed engine's slot is handed out again, so repeated sample() calls keep reusing the same stream and buffers."""
+    from occuspytial_b200 import LogitRSRGibbs
+    s = _rsr(LogitRSRGibbs, q=8)
+    a = s._make_engine(8, seed=1)
+    b = s._make_engine(8, seed=1)
+    assert a.slot != b.slot and a.stream.cuda_stream != b.stream.cuda_stream
+    slot_a, stream_a = a.slot, a.stream.cuda_stream
+    a.close()
+    c = s._make_engine(8, seed=1)
+    assert c.slot == slot_a and c.stream.cuda_stream == stream_a
+    b.close()
+    c.close()
