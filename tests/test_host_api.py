@@ -162,6 +162,26 @@ def test_reduced_summary_blocks_and_lazy_chain_summaries():
     np.testing.assert_array_equal(cs['a'], blocks)
 
 
+def test_engine_slots_are_exclusive_per_device():
+    """engine._acquire_slot / _release_slot: the lowest free slot of a device, never one that is in use (two engines alive
+    at the same time must not share a stream or a page-locked staging buffer), also under concurrent callers."""
+    from concurrent.futures import ThreadPoolExecutor
+    from occuspytial_b200 import engine
+    dev = 'cuda:77'   # a name no other test uses
+    a, b = engine._acquire_slot(dev), engine._acquire_slot(dev)
+    assert (a, b) == (0, 1) and engine._acquire_slot('cuda:78') == 0
+    engine._release_slot(dev, a)
+    assert engine._acquire_slot(dev) == 0 and engine._acquire_slot(dev) == 2
+    with ThreadPoolExecutor(8) as pool:
+        got = list(pool.map(lambda _: engine._acquire_slot(dev), range(64)))
+    assert len(set(got)) == 64 and not set(got) & {0, 1, 2}
+    for slot in got + [0, 1, 2]:
+        engine._release_slot(dev, slot)
+    engine._release_slot('cuda:78', 0)
+    assert engine._acquire_slot(dev) == 0
+    engine._release_slot(dev, 0)
+
+
 Q, W, X, y, *_ = (None,) * 5
 
 
