@@ -178,7 +178,8 @@ __device__ __forceinline__ bool icarw_chol8(const double* __restrict__ D, double
 // Rank-8 trailing update of one of the three update warps (HW = 0..2) for a compiled window size.  The tiles that stay
 // are named by their slot distances (ra, rb) from the pivot slot, 1 <= rb <= ra <= NT - 1, without (1, 1) (the next
 // pivot block, which warp 0 updates and factorises).  Whole ROWS ra are dealt to the warps, from the longest down in the
-// order 2 0 1 2 1 0 (NT = 8: 11 / 8 / 8 tiles; the last warp has no window rows to solve up to W = 64), so a warp reads
+// order 2 0 1 1 0 2 (NT = 8: 9 / 9 / 9 tiles: the last warp has no window rows to solve up to W = 64 but issues the
+// copies of the entering rows, which costs as much under load), so a warp reads
 // the panel fragment of its row once and executes exactly its own tiles -- the list is a compile-time constant.  (A lone
 // warp issues an instruction every ~6 cycles: the earlier version, which walked all NT (NT + 1) / 2 stored pairs under
 // predicates, spent 342 issue slots per step on the critical path of the factorisation.)
@@ -198,7 +199,7 @@ __device__ __forceinline__ void icarw_update_tiles(double* __restrict__ Ts, cons
 #pragma unroll
     for (int ra = NT - 1; ra >= 2; ra--) {
         const int k = (NT - 1 - ra) % 6;
-        const int owner = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 1 : (k == 3 ? 2 : (k == 4 ? 1 : 0))));
+        const int owner = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 1 : (k == 3 ? 1 : (k == 4 ? 0 : 2))));
         if (owner != HW) continue;
         const int sa = slot[ra];
         const double fa0 = p0[8 * sa], fa1 = p1[8 * sa];
