@@ -12,7 +12,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'occuspytial_b200
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True, check=True).stdout
 full = collections.Counter()
 for line in sass.splitlines():
-    m = re.match(r'\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_.]*)', line)
+    m = re.match(r'\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Za-z0-9_.]*)', line)
     if m:
         full[m.group(1)] += 1
 base = collections.Counter()
