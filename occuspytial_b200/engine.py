@@ -29,7 +29,7 @@ def _pinned_buffer(torch, device, slot, count, kind='h2d'):
     return buf[:count]
 
 
-_D2H_STAGING_MAX = 1 << 29   # results above 512 MiB take the plain pageable copy instead of a page-locked staging buffer
+_D2H_STAGING_MAX = 1 << 27   # results above 128 MiB take the plain pageable copy: page-locking (and keeping) that much host memory costs more than it saves on a run that long
 
 
 # ... and one CUDA stream per device and slot: torch's caching allocator keeps freed blocks per stream, so an engine that runs on
