@@ -417,8 +417,9 @@ struct SiteDebug {
 // Philox4x32-10 stream per draw, and also store omega_b and the occupancy probability.
 // ------------------------------------------------------------------------------------------------
 template <int R, bool F64, bool FUSE_PSI>
-// six CTAs per SM for r <= 3 (80 registers); the alpha partial sums alone are r (r + 3) / 2 doubles: fewer CTAs for larger r
-__global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : (R <= 3 ? 6 : (R <= 5 ? 4 : 3))) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
+// seven CTAs per SM for r <= 3 (72 registers: 1.11 ms at 4096 chains against 1.15 with six at 80 and 1.12 with eight at 64 and
+// spills); the alpha partial sums alone are r (r + 3) / 2 doubles: fewer CTAs for larger r
+__global__ void __launch_bounds__(CHAIN_TILE, F64 ? 1 : (R <= 3 ? 7 : (R <= 5 ? 4 : 3))) site_pass_probit_kernel(const View v, const SiteDebug dbg) {
     constexpr int NA = R * (R + 1) / 2, NV = NA + R;
     __shared__ __align__(16) float psi_s[FUSE_PSI ? SITE_TILE : 1][CHAIN_TILE];   // production engines only (FP32 psi)
     const int tid = threadIdx.x;
